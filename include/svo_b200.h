@@ -1,0 +1,95 @@
+/* svo_b200.h -- C ABI of libsvo_b200.so: the B200 (sm_100a CUDA) drop-in for the reference's
+ * device-runtime shim src/ocl.h and device code kernel/kernel.cl.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain C types only: handles are opaque pointers, sizes are bytes.  Like the reference
+ * (src/ocl.h:224-227) the launch state is global: ONE host thread drives ONE current context.
+ * Multi-GPU hosts create one context per device (svo_ctx_*) and switch the current one.
+ *
+ * Error behaviour: the reference aborts on every device error (CL_CHECK -> error_stop -> exit,
+ * src/ocl.h:29-41, src/error.h:2-12).  This library prints "svo_b200: ..." to stderr and
+ * abort()s, unless svo_set_error_mode(SVO_ERRORS_RETURN) was called, in which case the failing
+ * call returns / records a non-zero status readable with svo_last_error().
+ *
+ * There is no CPU fallback: without a CUDA device svo_init() fails.
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svo_mem_s *svo_mem_t;      /* replaces cl_mem      (device buffer handle; NULL is a valid "no buffer") */
+typedef struct svo_kernel_s *svo_kernel_t;/* replaces cl_kernel   (handle returned by svo_get_kernel)                */
+typedef struct svo_ctx_s *svo_ctx_t;      /* one per device: stream, scratch, compiled-in kernels                   */
+
+enum { SVO_ERRORS_ABORT = 0, SVO_ERRORS_RETURN = 1 };
+void        svo_set_error_mode(int mode);
+int         svo_last_error(void);           /* 0 = ok; cleared by svo_clear_error() */
+const char *svo_last_error_string(void);
+void        svo_clear_error(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int       svo_init(int device);             /* ocl_init()  src/ocl.h:57-146  (kernels are precompiled sm_100a, no source build) */
+void      svo_exit(void);                   /* ocl_exit()  src/ocl.h:168-174 */
+svo_ctx_t svo_ctx_create(int device);       /* extension: additional contexts for multi-GPU hosts */
+void      svo_ctx_destroy(svo_ctx_t ctx);
+void      svo_ctx_set_current(svo_ctx_t ctx);
+svo_ctx_t svo_ctx_get_current(void);
+int       svo_ctx_device(svo_ctx_t ctx);
+void     *svo_ctx_stream(svo_ctx_t ctx);    /* the cudaStream_t all launches of this context go to */
+int       svo_device_count(void);
+
+/* OCTREE_DEPTH is a compile-time constant of the reference (kernel/kernel.cl:12, src/octree/octree.h:2).
+ * Here it is a per-context setting; supported: 11 (reference) and 14.  Default 11. */
+void svo_set_octree_depth(int depth);
+int  svo_get_octree_depth(void);
+
+/* ---- memory ---------------------------------------------------------------------------------- */
+svo_mem_t svo_malloc(size_t size, const void *host_ptr);                 /* ocl_malloc()       src/ocl.h:200-213 (size 0 -> NULL) */
+void      svo_free(svo_mem_t mem);                                       /* clReleaseMemObject src/raycast.h:514 */
+void      svo_copy_to_host(void *dst, svo_mem_t src, size_t size, size_t srcofs); /* ocl_copy_to_host() src/ocl.h:215-221, blocking */
+void      svo_copy_to_device(svo_mem_t dst, size_t dstofs, const void *src, size_t size); /* extension (tests, scene upload), blocking */
+void      svo_memcpy(svo_mem_t dst, uint32_t dstofs, svo_mem_t src, uint32_t srcofs, uint32_t size); /* ocl_memcpy() src/ocl.h:285-297 */
+void      svo_memset(svo_mem_t dst, uint32_t dstofs, uint32_t val, uint32_t size);                   /* ocl_memset() src/ocl.h:299-309 */
+void     *svo_mem_device_ptr(svo_mem_t mem);                             /* raw device pointer (interop with other CUDA code) */
+size_t    svo_mem_size(svo_mem_t mem);
+
+/* ---- kernel launch (positional by-value arguments, exactly as the call sites in src/raycast.h) -- */
+/* names: memset memcpy raycast_proj raycast_counthole raycast_sumids raycast_writeids raycast_holes
+ *        raycast_fine_2 raycast_fillhole2 raycast_colorize; raycast_fillhole and raycast_fine resolve
+ *        but are the kernels the reference disables with if(0) (src/raycast.h:205,234): launching them is an error. */
+svo_kernel_t svo_get_kernel(const char *name);                           /* ocl_get_kernel() src/ocl.h:148-153 */
+void svo_begin(svo_kernel_t *kernel, int globalx, int globaly, int localx, int localy); /* ocl_begin() src/ocl.h:229-237 */
+void svo_param(size_t size, const void *ptr);                            /* ocl_param() src/ocl.h:238-241 */
+void svo_end(void);                                                      /* ocl_end()   src/ocl.h:268-274 (asynchronous) */
+void svo_begin_all_kernels(void);                                        /* ocl_begin_all_kernels() src/ocl.h:246-249 */
+void svo_end_all_kernels(void);                                          /* ocl_end_all_kernels()   src/ocl.h:253-265 (waits) */
+size_t svo_round_up(int group_size, int global_size);                    /* ocl_round_up() src/ocl.h:188-198 */
+uint64_t svo_launch_count(void);                                         /* CUDA kernels launched by this library so far */
+
+/* ---- fused frame (B200-native fast path; same results as the 13-launch sequence of
+ *      raycast_draw, src/raycast.h:147-438, without the mid-frame host readback) ------------------ */
+typedef struct svo_frame_params {
+    int   res_x, res_y, frame;
+    float v0[4];                 /* camera position (vec4f v0=pos, w=1)               src/raycast.h:159  */
+    float rows[3][4];            /* vx,vy,vz = rows of m    (raycast_proj)            src/raycast.h:160-162 */
+    float cols[3][4];            /* vx,vy,vz = columns of m (ray kernels)             src/raycast.h:322-325 */
+    float fovx, fovy;            /*                                                   src/raycast.h:109-110 */
+} svo_frame_params;
+
+/* One whole frame on buffers laid out as the reference's (4 colour + 4 coordinate buffers at stride
+ * res_x*res_y, id buffer, octree, colorize target).  Asynchronous; svo_end_all_kernels() waits.
+ * After it returns every buffer holds what the reference sequence would have left there. */
+void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t idbuffer, svo_mem_t octree,
+                     uint32_t octree_root, svo_mem_t screenbuffer_tex, const svo_frame_params *p);
+/* idbuf_size of the last fused frame (the value the reference reads back at src/raycast.h:298); blocking */
+int  svo_frame_idbuf_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,182 @@
+// ray.cuh -- SVO primary-ray traversal for sm_100a.
+//
+// Re-implements the ray state machine of the reference's CAST_RAY macro (kernel/kernel.cl:114-214)
+// and its node decoders fetchChildOffset (:32-62) / fetchColor (:64-112) so that the node visited at
+// every step -- and therefore the hit word 0xff000000+col and the hit position -- is bit-identical
+// to the reference executed with IEEE single precision (no FMA contraction: this translation unit is
+// compiled -fmad=false; / and sqrtf are the IEEE-rounded forms).
+//
+// B200 mapping: one ray per thread, rays of a warp cover an 8x4 (tile kernel) or 16x2 (hole kernel)
+// pixel footprint so the 32 descents share the upper tree levels; node words go through the read-only
+// path (ld.global.nc -> L1 -> L2: the 30..400 MB node pool lives in the 126 MB L2 for the reference scene);
+// the per-ray ancestor stack (D-1 words) is kept in shared memory transposed ([level][thread]) so the 32
+// lanes of a warp hit 32 different banks.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace svo {
+
+constexpr uint32_t kHole = 0xffffff00u;       // kernel/kernel.cl:267
+constexpr float kViewDistMax = 400000.0f;     // VIEW_DIST_MAX kernel/kernel.cl:15
+constexpr int kRayBlock = 256;                // threads per CTA of the ray kernels
+
+struct RayCam {                               // arguments shared by raycast_holes / raycast_fine_2
+    float m0x, m0y, m0z;                      // a_m0.xyz   camera position (world units)
+    float mxx, mxy, mxz;                      // a_mx.xyz   column 0 of m
+    float myx, myy, myz;                      // a_my.xyz
+    float mzx, mzy, mzz;                      // a_mz.xyz
+    float fovx, fovy;
+};
+
+__device__ __forceinline__ uint32_t ldg(const uint32_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t popc8(uint32_t v) { return __popc(v & 0xffu); }   // get_bitcount :23-29
+
+// fetchChildOffset, kernel/kernel.cl:32-62.  rekursion==1 never needs its load (the walk stops there and
+// fetchColor ignores the node id), so none is issued.
+__device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct, uint32_t node, uint32_t before,
+                                                uint32_t &local_root, uint32_t child, uint32_t child_test, int rekursion)
+{
+    uint32_t n = node >> 9, nadd = child;
+    if (node & 256u) {
+        if (!(before & 256u)) { local_root = n << 6; n = 0; }
+        n += local_root;
+        nadd = popc8(node & ((child_test << 1) - 1u));
+        if (rekursion == 2) return ((ldg(oct + n + (nadd >> 2)) >> ((nadd & 3u) << 3)) & 255u) + 256u + (nadd << 9);
+        if (rekursion == 1) return 0u;
+    }
+    return ldg(oct + n + nadd);
+}
+
+// sum of popcounts of bytes 1..n-1 of a byte-packed record (the loops at kernel/kernel.cl:82-85,104-107).
+// On a hit n <= 8, so the bytes sit in the record's first two words: one load per word instead of one per
+// byte.  (A ray that leaves the loop without a hit can arrive here with a meaningless n; the loop is still
+// exactly the reference's.)
+__device__ __forceinline__ uint32_t mask_bytes_popc(const uint32_t *__restrict__ rec, uint32_t n)
+{
+    uint32_t sum = 0, w = 0;
+    if (n > 1) w = ldg(rec);
+    for (uint32_t i = 1; i < n; ++i) {
+        if ((i & 3u) == 0) w = ldg(rec + (i >> 2));
+        sum += popc8(w >> ((i & 3u) << 3));
+    }
+    return sum;
+}
+
+// fetchColor, kernel/kernel.cl:64-112 (result intentionally unmasked: neighbouring bytes leak into bits 8..31)
+__device__ __forceinline__ uint32_t fetch_color(const uint32_t *__restrict__ oct, uint32_t node, uint32_t before,
+                                                uint32_t before2, uint32_t local_root, int rekursion, uint32_t child_test)
+{
+    uint32_t n = node >> 9, nadd = 8;
+    if (rekursion == 1) {
+        n = (before >> 9) & 15u;
+        const uint32_t ofs = (before2 >> 9) + local_root;
+        nadd = popc8(before2);
+        nadd += mask_bytes_popc(oct + ofs, n);
+        nadd += popc8(before & ((child_test << 1) - 1u));
+        return ldg(oct + ofs + (nadd >> 2)) >> ((nadd & 3u) << 3);
+    }
+    if (node & 256u) {
+        if (!(before & 256u)) { local_root = n << 6; n = 0; }
+        nadd = local_root;
+        if (rekursion == 2) {
+            const uint32_t ofs = (before >> 9) + local_root;
+            nadd = 1 + popc8(before);
+            nadd += mask_bytes_popc(oct + ofs, n);
+            return ldg(oct + ofs + (nadd >> 2)) >> ((nadd & 3u) << 3);
+        }
+    }
+    return ldg(oct + n + nadd);
+}
+
+// One primary ray for pixel (idx, idy): ray set-up of raycast_holes :639-663 / raycast_fine_2 :883-908,
+// CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
+// `stack` points at this thread's column of the shared [D+1][kRayBlock] array.
+template <int D>
+__device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
+                                            const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
+                                            int idx, int idy, const RayCam &c, uint32_t *stack)
+{
+    constexpr int kScaleMax = 1 << (D + 1);            // SCALE_MAX :19
+    constexpr int kDepthAnd = (1 << D) - 1;            // OCTREE_DEPTH_AND :13
+    const float d1x = ((float)(idx - res_x / 2) + 0.5f) * c.fovx / (float)res_y;   // exact: |int|+0.5 fits binary32
+    const float d1y = ((float)(idy - res_y / 2) + 0.5f) * c.fovy / (float)res_y;
+    float dx = d1x * c.mxx + d1y * c.mxy + c.mxz;      // dot(delta1, a_mx.xyz), delta1.z = 1
+    float dy = d1x * c.myx + d1y * c.myy + c.myz;
+    float dz = d1x * c.mzx + d1y * c.mzy + c.mzz;
+    float px = c.m0x * 16.0f, py = c.m0y * 16.0f, pz = c.m0z * 16.0f;
+
+    const float eps = 9.5367431640625e-07f;            // pow(2,-20) :118
+    if (fabsf(dx) < eps) dx = (dx > 0.f ? 1.f : (dx < 0.f ? -1.f : 0.f)) * eps;
+    if (fabsf(dy) < eps) dy = (dy > 0.f ? 1.f : (dy < 0.f ? -1.f : 0.f)) * eps;
+    if (fabsf(dz) < eps) dz = (dz > 0.f ? 1.f : (dz < 0.f ? -1.f : 0.f)) * eps;
+    int sign_xyz = 0;
+    if (dx < 0.f) { sign_xyz |= 1; px = (float)kScaleMax - px; dx = -dx; }
+    if (dy < 0.f) { sign_xyz |= 2; py = (float)kScaleMax - py; dy = -dy; }
+    if (dz < 0.f) { sign_xyz |= 4; pz = (float)kScaleMax - pz; dz = -dz; }
+    const float g0y = dy / dx, g0z = dz / dx;
+    const float g1x = dx / dy, g1z = dz / dy;
+    const float g2x = dx / dz, g2y = dy / dz;
+    const float len0 = sqrtf(1.0f + g0y * g0y + g0z * g0z);
+    const float len1 = sqrtf(g1x * g1x + 1.0f + g1z * g1z);
+    const float len2 = sqrtf(g2x * g2x + g2y * g2y + 1.0f);
+
+    int ix = __float2int_rz(px), iy = __float2int_rz(py), iz = __float2int_rz(pz);
+    uint32_t nodeid = root, before = root, local_root = 0, node_test = 0;
+    int rekursion = D, lod = 1, x0ry = 0;
+    float distance = 0.f, lodswitch = (float)(res_x * 2);          // res_x*LOD_ADJUST*2 :663
+    int guard = 1 << 20;                                           // never reached; bounds a corrupt octree
+
+    do {
+        const int cx = ix >> rekursion, cy = iy >> rekursion, cz = iz >> rekursion;
+        const int node_index = ((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) ^ sign_xyz;
+        node_test = nodeid & (1u << node_index);
+        if (node_test) {
+            const uint32_t tmp = nodeid;
+            nodeid = fetch_child(oct, nodeid, before, local_root, (uint32_t)node_index, node_test, rekursion);
+            before = tmp;
+            if (rekursion <= lod) break;
+            --rekursion;
+            stack[rekursion * kRayBlock] = nodeid;
+            continue;
+        }
+        const float mx = (float)((cx + 1) << rekursion) - px;
+        const float my = (float)((cy + 1) << rekursion) - py;
+        const float mz = (float)((cz + 1) << rekursion) - pz;
+        float dist = mx * len0;
+        float sx = mx, sy = g0y * mx, sz = g0z * mx;
+        const float dist_y = my * len1, dist_z = mz * len2;
+        if (dist_y < dist) { dist = dist_y; sx = g1x * my; sy = my; sz = g1z * my; }
+        if (dist_z < dist) { dist = dist_z; sx = g2x * mz; sy = g2y * mz; sz = mz; }
+        px += sx; py += sy; pz += sz;
+        const int nx = __float2int_rz(px), ny = __float2int_rz(py), nz = __float2int_rz(pz);
+        distance += dist;
+        x0ry = iy ^ ny;
+        const int x0r = ((ix ^ nx) ^ x0ry ^ (iz ^ nz)) & kDepthAnd;
+        ix = nx; iy = ny; iz = nz;
+        if (distance > kViewDistMax) break;
+        // (int)log2((float)x0r): floor(log2) for x0r>0, INT_MIN for 0  ->  "x0r < 2^rekursion" means stay
+        if ((x0r >> rekursion) == 0) continue;
+        rekursion = 32 - __clz(x0r);                               // rekursion_new + 1
+        if (rekursion >= D) { nodeid = before = root; }
+        else {
+            nodeid = stack[rekursion * kRayBlock];
+            before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * kRayBlock];
+        }
+        if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }
+    } while (!(x0ry & (2 * kDepthAnd + 2)) && --guard);
+
+    if (sign_xyz & 1) px = (float)kScaleMax - px;
+    if (sign_xyz & 2) py = (float)kScaleMax - py;
+    if (sign_xyz & 4) pz = (float)kScaleMax - pz;
+
+    const uint32_t before2 = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * kRayBlock];
+    const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
+    const size_t ofs = (size_t)idy * res_x + idx;
+    screen[ofs] = 0xff000000u + col;
+    float2 *b2 = reinterpret_cast<float2 *>(back + ofs * 4);
+    *b2 = make_float2(px / 16.0f, py / 16.0f);
+    back[ofs * 4 + 2] = pz / 16.0f;
+}
+
+}  // namespace svo

@@ -1,0 +1,604 @@
+// svo_abi.cu -- the C ABI of libsvo_b200.so (include/svo_b200.h): context, device memory, and the
+// ocl_begin / ocl_param / ocl_end style launch marshalling of the reference's src/ocl.h, dispatching to the
+// hand-written sm_100a kernels in ray.cuh / warp.cuh.  No OpenCL, no run-time source build, no CPU fallback.
+#include "../../include/svo_b200.h"
+#include "ray.cuh"
+#include "warp.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace svo;
+
+// ------------------------------------------------------------------------------------------------
+// errors: fatal by default, like CL_CHECK -> error_stop (src/ocl.h:29-41, src/error.h:2-12)
+// ------------------------------------------------------------------------------------------------
+static int g_error_mode = SVO_ERRORS_ABORT;
+static int g_last_error = 0;
+static char g_last_error_str[512] = "";
+
+static void svo_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error_str, sizeof g_last_error_str, fmt, ap);
+    va_end(ap);
+    g_last_error = code ? code : -1;
+    fprintf(stderr, "svo_b200: error %d: %s\n", g_last_error, g_last_error_str);
+    if (g_error_mode == SVO_ERRORS_ABORT) abort();
+}
+
+#define CU_CHECK(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) svo_fail((int)_e, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+    } while (0)
+
+extern "C" void svo_set_error_mode(int mode) { g_error_mode = mode; }
+extern "C" int svo_last_error(void) { return g_last_error; }
+extern "C" const char *svo_last_error_string(void) { return g_last_error_str; }
+extern "C" void svo_clear_error(void) { g_last_error = 0; g_last_error_str[0] = 0; }
+
+// ------------------------------------------------------------------------------------------------
+// context / memory
+// ------------------------------------------------------------------------------------------------
+struct svo_mem_s {
+    void *dptr;
+    size_t bytes;
+    int device;
+};
+
+struct svo_ctx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int depth = 11;
+    unsigned long long *key = nullptr;      // reprojection keys, one per destination pixel, kept armed (all ones)
+    size_t key_pixels = 0;
+    uint32_t *snap = nullptr;               // fillhole2 snapshot
+    size_t snap_words = 0;
+    uint64_t launches = 0;
+    int last_idbuf_words = 0;               // 2*B of the last fused frame (where idb[0] holds the total)
+    svo_mem_t last_idbuf = nullptr;
+};
+
+static svo_ctx_t g_ctx = nullptr;           // current context (the reference's globals, src/ocl.h:8-16)
+
+static svo_ctx_t need_ctx()
+{
+    if (!g_ctx) svo_fail(-100, "no context: call svo_init() first");
+    return g_ctx;
+}
+
+extern "C" int svo_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" svo_ctx_t svo_ctx_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        svo_fail(-101, "no CUDA device available (%s): this library has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { svo_fail(-102, "device %d out of range (%d devices)", device, n); return nullptr; }
+    svo_ctx_t c = new svo_ctx_s();
+    c->device = device;
+    CU_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    return c;
+}
+
+extern "C" void svo_ctx_destroy(svo_ctx_t c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->key) cudaFree(c->key);
+    if (c->snap) cudaFree(c->snap);
+    cudaStreamDestroy(c->stream);
+    if (g_ctx == c) g_ctx = nullptr;
+    delete c;
+}
+
+extern "C" void svo_ctx_set_current(svo_ctx_t c)
+{
+    g_ctx = c;
+    if (c) CU_CHECK(cudaSetDevice(c->device));
+}
+extern "C" svo_ctx_t svo_ctx_get_current(void) { return g_ctx; }
+extern "C" int svo_ctx_device(svo_ctx_t c) { return c ? c->device : -1; }
+extern "C" void *svo_ctx_stream(svo_ctx_t c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int svo_init(int device)
+{
+    svo_ctx_t c = svo_ctx_create(device);
+    if (!c) return g_last_error ? g_last_error : -1;
+    svo_ctx_set_current(c);
+    return 0;
+}
+
+extern "C" void svo_exit(void)
+{
+    if (g_ctx) svo_ctx_destroy(g_ctx);
+    g_ctx = nullptr;
+}
+
+extern "C" void svo_set_octree_depth(int depth)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (depth != 11 && depth != 14) { svo_fail(-103, "unsupported OCTREE_DEPTH %d (supported: 11, 14)", depth); return; }
+    c->depth = depth;
+}
+extern "C" int svo_get_octree_depth(void) { return g_ctx ? g_ctx->depth : 11; }
+
+extern "C" svo_mem_t svo_malloc(size_t size, const void *host_ptr)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || size == 0) return nullptr;                             // src/ocl.h:203
+    svo_mem_t m = new svo_mem_s{nullptr, size, c->device};
+    // 256 B of slack: the reference's fetch loops may read a few words past the last octree record
+    CU_CHECK(cudaMalloc(&m->dptr, size + 256));
+    if (!m->dptr) { delete m; return nullptr; }
+    if (host_ptr) CU_CHECK(cudaMemcpyAsync(m->dptr, host_ptr, size, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync((char *)m->dptr + size, 0, 256, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));                      // CL_MEM_COPY_HOST_PTR copies at creation
+    return m;
+}
+
+extern "C" void svo_free(svo_mem_t m)
+{
+    if (!m) return;
+    if (g_ctx) cudaStreamSynchronize(g_ctx->stream);
+    cudaFree(m->dptr);
+    delete m;
+}
+
+extern "C" void *svo_mem_device_ptr(svo_mem_t m) { return m ? m->dptr : nullptr; }
+extern "C" size_t svo_mem_size(svo_mem_t m) { return m ? m->bytes : 0; }
+
+extern "C" void svo_copy_to_host(void *dst, svo_mem_t src, size_t size, size_t srcofs)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!src || srcofs + size > src->bytes) { svo_fail(-104, "svo_copy_to_host out of range"); return; }
+    CU_CHECK(cudaMemcpyAsync(dst, (const char *)src->dptr + srcofs, size, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+extern "C" void svo_copy_to_device(svo_mem_t dst, size_t dstofs, const void *src, size_t size)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!dst || dstofs + size > dst->bytes) { svo_fail(-105, "svo_copy_to_device out of range"); return; }
+    CU_CHECK(cudaMemcpyAsync((char *)dst->dptr + dstofs, src, size, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+extern "C" size_t svo_round_up(int group_size, int global_size)       // src/ocl.h:188-198
+{
+    const int r = global_size % group_size;
+    return r == 0 ? (size_t)global_size : (size_t)(global_size + group_size - r);
+}
+
+extern "C" uint64_t svo_launch_count(void) { return g_ctx ? g_ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static inline int bw_grid(svo_ctx_t c, size_t items, int block = 256, int per_sm = 8)
+{
+    size_t g = (items + block - 1) / block;
+    const size_t cap = (size_t)c->num_sms * per_sm;
+    if (g > cap) g = cap;
+    return g ? (int)g : 1;
+}
+
+#define LAUNCHED(c)                                   \
+    do {                                              \
+        (c)->launches++;                              \
+        CU_CHECK(cudaGetLastError());                 \
+    } while (0)
+
+static void ensure_key(svo_ctx_t c, size_t pixels)
+{
+    if (c->key_pixels >= pixels) return;
+    if (c->key) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->key)); }
+    CU_CHECK(cudaMalloc(&c->key, pixels * 8));
+    CU_CHECK(cudaMemsetAsync(c->key, 0xff, pixels * 8, c->stream));
+    c->key_pixels = pixels;
+}
+
+static void ensure_snap(svo_ctx_t c, size_t words)
+{
+    if (c->snap_words >= words) return;
+    if (c->snap) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->snap)); }
+    CU_CHECK(cudaMalloc(&c->snap, words * 4));
+    c->snap_words = words;
+}
+
+static void do_memset(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, uint32_t val, uint32_t nwords)
+{
+    if (!nwords) return;
+    k_memset<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, val, nwords);
+    LAUNCHED(c);
+}
+
+static void do_memcpy(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, const uint32_t *src, uint32_t srcofs, uint32_t nwords)
+{
+    if (!nwords) return;
+    k_memcpy<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, src, srcofs, nwords);
+    LAUNCHED(c);
+}
+
+static ProjCam make_proj_cam(const float *m0, const float *mx, const float *my, const float *mz)
+{
+    return ProjCam{m0[0], m0[1], m0[2], mx[0], mx[1], mx[2], my[0], my[1], my[2], mz[0], mz[1], mz[2]};
+}
+static RayCam make_ray_cam(const float *m0, const float *mx, const float *my, const float *mz, float fovx, float fovy)
+{
+    return RayCam{m0[0], m0[1], m0[2], mx[0], mx[1], mx[2], my[0], my[1], my[2], mz[0], mz[1], mz[2], fovx, fovy};
+}
+
+static void do_proj_scatter(svo_ctx_t c, uint32_t *screen, float *back, int res_x, int res_y, int ofs_add, const ProjCam &cam)
+{
+    const size_t n = (size_t)res_x * res_y;
+    ensure_key(c, n);
+    k_proj_scatter<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, ofs_add, cam);
+    LAUNCHED(c);
+}
+static void do_proj_resolve(svo_ctx_t c, uint32_t *screen, float *back, int res_x, int res_y, const ProjCam &cam)
+{
+    const size_t n = (size_t)res_x * res_y;
+    k_proj_resolve<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, cam);
+    LAUNCHED(c);
+}
+
+static void do_counthole(svo_ctx_t c, const uint32_t *screen, uint32_t *idb, int res_x, int res_y)
+{
+    const int nb = (res_x / 16) * (res_y / 16);
+    if (!nb) return;
+    k_counthole<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y);
+    LAUNCHED(c);
+}
+static void do_sumids(svo_ctx_t c, uint32_t *idb, int res_x, int res_y)
+{
+    k_sumids<<<1, 1024, 0, c->stream>>>(idb, (res_x / 16) * (res_y / 16));
+    LAUNCHED(c);
+}
+static void do_writeids(svo_ctx_t c, const uint32_t *screen, uint32_t *idb, int res_x, int res_y)
+{
+    const int nb = (res_x / 16) * (res_y / 16);
+    if (!nb) return;
+    k_writeids<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y);
+    LAUNCHED(c);
+}
+
+// size_ptr != nullptr: idbuf_size is read on the device and the grid is a fixed persistent one
+static void do_holes(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t *oct, const uint32_t *idb,
+                     const uint32_t *size_ptr, uint32_t root, int res_x, int res_y, int idbuf_size, const RayCam &cam)
+{
+    int grid;
+    if (size_ptr) grid = c->num_sms * 8;
+    else {
+        if (idbuf_size <= 0) return;
+        grid = (idbuf_size + kRayBlock - 1) / kRayBlock;
+    }
+    if (c->depth == 11)
+        k_raycast_holes<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, idb, size_ptr, root, res_x, res_y, idbuf_size, cam);
+    else
+        k_raycast_holes<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, idb, size_ptr, root, res_x, res_y, idbuf_size, cam);
+    LAUNCHED(c);
+}
+
+static void do_fine_2(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t *oct, uint32_t root, int res_x, int res_y,
+                      int gx, int gy, int add_x, int add_y, const RayCam &cam)
+{
+    if (gx <= 0 || gy <= 0) return;
+    dim3 grid((gx + 31) / 32, (gy + 7) / 8);
+    if (c->depth == 11)
+        k_raycast_fine_2<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
+    else
+        k_raycast_fine_2<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
+    LAUNCHED(c);
+}
+
+// snapshot source: `snap_src` if the caller knows a buffer with the same content (fused frame: the cache copy),
+// else an internal copy of the image (+ the words the 5x5 search can reach past it).
+static void do_fillhole2(svo_ctx_t c, uint32_t *screen, const uint32_t *snap_src, int res_x, int res_y, size_t avail_words)
+{
+    const size_t n = (size_t)res_x * res_y;
+    const uint32_t *snap = snap_src;
+    if (!snap) {
+        size_t words = n + 2 * (size_t)res_x + 4;
+        if (words > avail_words) words = avail_words;
+        ensure_snap(c, words);
+        do_memcpy(c, c->snap, 0, screen, 0, (uint32_t)words);
+        snap = c->snap;
+    }
+    k_fillhole2<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, snap, res_x, res_y);
+    LAUNCHED(c);
+}
+
+static void do_colorize(svo_ctx_t c, const uint32_t *screen, uint32_t *tex, int w, int h)
+{
+    const size_t n = (size_t)w * h;
+    if (!n) return;
+    k_colorize<<<bw_grid(c, (n + 3) / 4), 256, 0, c->stream>>>(screen, tex, (int)n);
+    LAUNCHED(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ocl_memcpy / ocl_memset (src/ocl.h:285-309): byte offsets and sizes, 4-byte granularity, and the
+// kernel's global size is rounded up to a multiple of 256 work items like every ocl_begin().
+// The rounded-up tail is clamped to the allocation so it can never write outside the buffer.
+// ------------------------------------------------------------------------------------------------
+static uint32_t clamp_words(svo_mem_t m, uint32_t ofs_words, uint32_t nwords)
+{
+    const size_t total = m->bytes / 4;
+    if (ofs_words >= total) return 0;
+    return (size_t)ofs_words + nwords > total ? (uint32_t)(total - ofs_words) : nwords;
+}
+
+extern "C" void svo_memcpy(svo_mem_t dst, uint32_t dstofs, svo_mem_t src, uint32_t srcofs, uint32_t size)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!dst || !src) { svo_fail(-106, "svo_memcpy: null buffer"); return; }
+    srcofs /= 4; dstofs /= 4; size /= 4;
+    uint32_t n = (uint32_t)svo_round_up(256, (int)size);
+    n = clamp_words(dst, dstofs, n);
+    n = clamp_words(src, srcofs, n);
+    do_memcpy(c, (uint32_t *)dst->dptr, dstofs, (const uint32_t *)src->dptr, srcofs, n);
+}
+
+extern "C" void svo_memset(svo_mem_t dst, uint32_t dstofs, uint32_t val, uint32_t size)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!dst) { svo_fail(-107, "svo_memset: null buffer"); return; }
+    dstofs /= 4; size /= 4;
+    uint32_t n = clamp_words(dst, dstofs, (uint32_t)svo_round_up(256, (int)size));
+    do_memset(c, (uint32_t *)dst->dptr, dstofs, val, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels by name + positional argument marshalling
+// ------------------------------------------------------------------------------------------------
+enum KernelId {
+    K_MEMSET, K_MEMCPY, K_PROJ, K_COUNTHOLE, K_SUMIDS, K_WRITEIDS, K_HOLES, K_FINE_2, K_FILLHOLE2, K_COLORIZE,
+    K_FILLHOLE_DISABLED, K_FINE_DISABLED, K_COUNT
+};
+enum ArgKind : unsigned char { A_MEM, A_I32, A_F4, A_F1, A_F4_DEAD };   // A_F4_DEAD: float4 the kernels never read (not copied)
+
+struct svo_kernel_s {
+    KernelId id;
+    const char *name;
+    int nargs;
+    ArgKind args[24];
+};
+
+static svo_kernel_s g_kernels[K_COUNT] = {
+    {K_MEMSET, "memset", 3, {A_MEM, A_I32, A_I32}},                                                  // src/ocl.h:305-307
+    {K_MEMCPY, "memcpy", 4, {A_MEM, A_I32, A_MEM, A_I32}},                                           // src/ocl.h:292-295
+    {K_PROJ, "raycast_proj", 13, {A_MEM, A_MEM, A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32, A_I32, A_F4, A_F4, A_F4, A_F4}},  // src/raycast.h:184-196
+    {K_COUNTHOLE, "raycast_counthole", 6, {A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32}},               // src/raycast.h:275-280
+    {K_SUMIDS, "raycast_sumids", 6, {A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32}},                     // src/raycast.h:290-295
+    {K_WRITEIDS, "raycast_writeids", 6, {A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32}},                 // src/raycast.h:308-313
+    {K_HOLES, "raycast_holes", 22, {A_MEM, A_MEM, A_MEM, A_MEM, A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32, A_I32, A_I32,
+                                    A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4, A_F4, A_F4, A_F4, A_F1, A_F1}},       // src/raycast.h:336-357
+    {K_FINE_2, "raycast_fine_2", 19, {A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32, A_I32, A_I32, A_I32,
+                                      A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4, A_F4, A_F4, A_F4, A_F1, A_F1}},     // src/raycast.h:367-385
+    {K_FILLHOLE2, "raycast_fillhole2", 5, {A_MEM, A_MEM, A_I32, A_I32, A_I32}},                      // src/raycast.h:416-420
+    {K_COLORIZE, "raycast_colorize", 4, {A_MEM, A_MEM, A_I32, A_I32}},                               // src/raycast.h:432-435
+    {K_FILLHOLE_DISABLED, "raycast_fillhole", 0, {}},                                                // disabled: src/raycast.h:205
+    {K_FINE_DISABLED, "raycast_fine", 0, {}},                                                        // disabled: src/raycast.h:234
+};
+
+extern "C" svo_kernel_t svo_get_kernel(const char *name)
+{
+    need_ctx();
+    for (int i = 0; i < K_COUNT; ++i)
+        if (name && !strcmp(name, g_kernels[i].name)) return &g_kernels[i];
+    svo_fail(-46, "CL_INVALID_KERNEL_NAME: no kernel named '%s'", name ? name : "(null)");
+    return nullptr;
+}
+
+// global launch state, as in src/ocl.h:224-227
+struct ArgSlot { size_t size; unsigned char bytes[16]; };
+static int g_narg = 0;
+static ArgSlot g_args[32];
+static size_t g_global[2], g_local[2];
+static svo_kernel_t g_current = nullptr;
+
+extern "C" void svo_begin(svo_kernel_t *kernel, int globalx, int globaly, int localx, int localy)
+{
+    g_narg = 0;
+    g_local[0] = localx; g_local[1] = localy;
+    g_global[0] = svo_round_up(localx, globalx);
+    g_global[1] = svo_round_up(localy, globaly);
+    g_current = kernel ? *kernel : nullptr;
+    if (!g_current) svo_fail(-48, "CL_INVALID_KERNEL: svo_begin with a null kernel");
+}
+
+extern "C" void svo_param(size_t size, const void *ptr)
+{
+    if (!g_current) return;
+    if (g_narg >= 32 || size > 16) { svo_fail(-51, "CL_INVALID_ARG_SIZE: argument %d has %zu bytes", g_narg, size); return; }
+    ArgSlot &s = g_args[g_narg];
+    s.size = size;
+    const bool dead = g_narg < g_current->nargs && g_current->args[g_narg] == A_F4_DEAD;
+    if (!dead && ptr) memcpy(s.bytes, ptr, size);      // dead float4s point at 12-byte vec3f's in the reference: never read
+    else memset(s.bytes, 0, sizeof s.bytes);
+    g_narg++;
+}
+
+template <class T>
+static T arg(int i) { T v; memcpy(&v, g_args[i].bytes, sizeof(T)); return v; }
+static uint32_t *arg_u32p(int i) { svo_mem_t m = arg<svo_mem_t>(i); return m ? (uint32_t *)m->dptr : nullptr; }
+static float *arg_f32p(int i) { svo_mem_t m = arg<svo_mem_t>(i); return m ? (float *)m->dptr : nullptr; }
+static const float *arg_f4(int i) { return reinterpret_cast<const float *>(g_args[i].bytes); }
+
+extern "C" void svo_end(void)
+{
+    svo_ctx_t c = need_ctx();
+    svo_kernel_t k = g_current;
+    if (!c || !k) return;
+    if (k->id == K_FILLHOLE_DISABLED || k->id == K_FINE_DISABLED) {
+        svo_fail(-59, "CL_INVALID_OPERATION: kernel '%s' is disabled in the reference (if(0)) and not provided", k->name);
+        return;
+    }
+    if (g_narg != k->nargs) { svo_fail(-52, "CL_INVALID_KERNEL_ARGS: '%s' takes %d arguments, %d given", k->name, k->nargs, g_narg); return; }
+    for (int i = 0; i < k->nargs; ++i) {
+        static const size_t want[] = {sizeof(void *), 4, 16, 4, 16};
+        if (g_args[i].size != want[k->args[i]]) {
+            svo_fail(-51, "CL_INVALID_ARG_SIZE: '%s' argument %d: %zu bytes given, %zu expected", k->name, i, g_args[i].size, want[k->args[i]]);
+            return;
+        }
+    }
+    const int gx = (int)g_global[0], gy = (int)g_global[1];
+    switch (k->id) {
+    case K_MEMSET: {
+        svo_mem_t m = arg<svo_mem_t>(0);
+        if (!m) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: memset"); return; }
+        do_memset(c, (uint32_t *)m->dptr, arg<uint32_t>(1), arg<uint32_t>(2), clamp_words(m, arg<uint32_t>(1), (uint32_t)gx));
+        break;
+    }
+    case K_MEMCPY: {
+        svo_mem_t d = arg<svo_mem_t>(0), s = arg<svo_mem_t>(2);
+        if (!d || !s) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: memcpy"); return; }
+        uint32_t n = clamp_words(d, arg<uint32_t>(1), (uint32_t)gx);
+        n = clamp_words(s, arg<uint32_t>(3), n);
+        do_memcpy(c, (uint32_t *)d->dptr, arg<uint32_t>(1), (const uint32_t *)s->dptr, arg<uint32_t>(3), n);
+        break;
+    }
+    case K_PROJ: {
+        uint32_t *screen = arg_u32p(0); float *back = arg_f32p(1);
+        if (!screen || !back) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_proj"); return; }
+        const int res_x = arg<int>(5), res_y = arg<int>(6), ofs_add = arg<int>(8);
+        const ProjCam cam = make_proj_cam(arg_f4(9), arg_f4(10), arg_f4(11), arg_f4(12));
+        do_proj_scatter(c, screen, back, res_x, res_y, ofs_add, cam);
+        do_proj_resolve(c, screen, back, res_x, res_y, cam);
+        break;
+    }
+    case K_COUNTHOLE:
+    case K_SUMIDS:
+    case K_WRITEIDS: {
+        uint32_t *screen = arg_u32p(0), *idb = arg_u32p(2);
+        if (!screen || !idb) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: %s", k->name); return; }
+        const int res_x = arg<int>(3), res_y = arg<int>(4);
+        if (k->id == K_COUNTHOLE) do_counthole(c, screen, idb, res_x, res_y);
+        else if (k->id == K_SUMIDS) do_sumids(c, idb, res_x, res_y);
+        else do_writeids(c, screen, idb, res_x, res_y);
+        break;
+    }
+    case K_HOLES: {
+        uint32_t *screen = arg_u32p(0); float *back = arg_f32p(1);
+        const uint32_t *oct = arg_u32p(2), *idb = arg_u32p(6);
+        if (!screen || !back || !oct || !idb) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_holes"); return; }
+        const int res_x = arg<int>(8), res_y = arg<int>(9), idbuf_size = arg<int>(11);
+        const RayCam cam = make_ray_cam(arg_f4(16), arg_f4(17), arg_f4(18), arg_f4(19), arg<float>(20), arg<float>(21));
+        do_holes(c, screen, back, oct, idb, nullptr, arg<uint32_t>(7), res_x, res_y, idbuf_size < gx ? idbuf_size : gx, cam);
+        break;
+    }
+    case K_FINE_2: {
+        uint32_t *screen = arg_u32p(0); float *back = arg_f32p(1);
+        const uint32_t *oct = arg_u32p(2);
+        if (!screen || !back || !oct) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_fine_2"); return; }
+        const int res_x = arg<int>(4), res_y = arg<int>(5), add_x = arg<int>(7), add_y = arg<int>(8);
+        const RayCam cam = make_ray_cam(arg_f4(13), arg_f4(14), arg_f4(15), arg_f4(16), arg<float>(17), arg<float>(18));
+        do_fine_2(c, screen, back, oct, arg<uint32_t>(3), res_x, res_y, gx, gy, add_x, add_y, cam);
+        break;
+    }
+    case K_FILLHOLE2: {
+        svo_mem_t m = arg<svo_mem_t>(0);
+        if (!m) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_fillhole2"); return; }
+        do_fillhole2(c, (uint32_t *)m->dptr, nullptr, arg<int>(2), arg<int>(3), m->bytes / 4);
+        break;
+    }
+    case K_COLORIZE: {
+        uint32_t *screen = arg_u32p(0), *tex = arg_u32p(1);
+        if (!screen || !tex) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_colorize"); return; }
+        do_colorize(c, screen, tex, arg<int>(2), arg<int>(3));
+        break;
+    }
+    default: break;
+    }
+}
+
+extern "C" void svo_begin_all_kernels(void) {}                        // src/ocl.h:246-249 (resets the event list)
+
+extern "C" void svo_end_all_kernels(void)                             // src/ocl.h:253-265: wait for the last kernel
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused frame: the launch sequence of raycast_draw (src/raycast.h:147-438) without the mid-frame host
+// readback (idbuf_size stays on the device and the hole raycast is a persistent grid), with one
+// reprojection scatter per source buffer resolved once (keys carry the source offset, so buffer 1 beats
+// buffer 2 on ties exactly like the two serial launches), and with the small-gap filter reading its
+// snapshot from the cache copy that was just made (buffer 2 == pre-filter buffer 0).
+// ------------------------------------------------------------------------------------------------
+extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t idbuffer, svo_mem_t octree,
+                                uint32_t octree_root, svo_mem_t screenbuffer_tex, const svo_frame_params *p)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!screenbuffer || !backbuffer || !idbuffer || !octree || !p) { svo_fail(-38, "svo_frame_fused: null argument"); return; }
+    const int res_x = p->res_x, res_y = p->res_y, frame = p->frame;
+    const uint32_t n = (uint32_t)res_x * (uint32_t)res_y;
+    const int nb = (res_x / 16) * (res_y / 16);
+    if ((size_t)n * 16 > screenbuffer->bytes || (size_t)n * 64 > backbuffer->bytes || ((size_t)n + 2 * nb) * 4 > idbuffer->bytes) {
+        svo_fail(-61, "svo_frame_fused: buffers too small for %dx%d", res_x, res_y);
+        return;
+    }
+    uint32_t *screen = (uint32_t *)screenbuffer->dptr;
+    float *back = (float *)backbuffer->dptr;
+    uint32_t *idb = (uint32_t *)idbuffer->dptr;
+    const uint32_t *oct = (const uint32_t *)octree->dptr;
+
+    if (frame < 2) do_memset(c, screen, 0, kHole, n * 4);                     // :150-154
+    do_memset(c, screen, 0, kHole, n);                                        // :157
+    const ProjCam pc = make_proj_cam(p->v0, p->rows[0], p->rows[1], p->rows[2]);
+    do_proj_scatter(c, screen, back, res_x, res_y, (int)n, pc);               // :177-198, source buffer 1
+    do_proj_scatter(c, screen, back, res_x, res_y, (int)(2 * n), pc);         //           source buffer 2
+    do_proj_resolve(c, screen, back, res_x, res_y, pc);
+    do_counthole(c, screen, idb, res_x, res_y);                               // :272-282
+    do_sumids(c, idb, res_x, res_y);                                          // :287-296 (no readback)
+    do_writeids(c, screen, idb, res_x, res_y);                                // :305-315
+    const RayCam rc = make_ray_cam(p->v0, p->cols[0], p->cols[1], p->cols[2], p->fovx, p->fovy);
+    do_holes(c, screen, back, oct, idb, idb, octree_root, res_x, res_y, 0, rc);   // :332-359, size = idb[0] on device
+    const int add_x = (res_x / 8) * (frame & 7), add_y = (res_y / 4) * ((frame >> 3) & 3);   // :363-364
+    do_fine_2(c, screen, back, oct, octree_root, res_x, res_y, (int)svo_round_up(16, res_x / 8), (int)svo_round_up(16, res_y / 4),
+              add_x, add_y, rc);                                              // :365-386
+    do_memcpy(c, screen, 2 * n, screen, 0, n);                                // :394-405 (target = 2)
+    do_memcpy(c, (uint32_t *)back, 2 * n * 4, (const uint32_t *)back, 0, n * 4);
+    // :411-422; rows past the image are read from buffer 1 in the reference and from buffer 3 through the
+    // buffer-2 snapshot here: both are all-holes (nothing ever writes them), see DESIGN.md
+    do_fillhole2(c, screen, nullptr, res_x, res_y, screenbuffer->bytes / 4);
+    if (screenbuffer_tex) do_colorize(c, screen, (uint32_t *)screenbuffer_tex->dptr, res_x, res_y);   // :429-437
+    c->last_idbuf = idbuffer;
+}
+
+extern "C" int svo_frame_idbuf_size(void)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || !c->last_idbuf) return 0;
+    int v = 0;
+    svo_copy_to_host(&v, c->last_idbuf, 4, 0);
+    return v;
+}

@@ -1,0 +1,242 @@
+"""Python mirror of the reference's frame driver src/raycast.h on top of ocl.py (-> libsvo_b200.so).
+
+Same entry points and call sequence as the reference: ``raycast_init()`` (:61-91), ``raycast_draw(res_x, res_y)``
+(:93-510), ``raycast_exit()`` (:511-517).  What the window supplied in the reference (MOUSE_X/Y -> rot,
+WASD -> pos, :113-133) is set explicitly with ``set_camera(pos, rot)``; the GL blit (:449-472) is replaced by
+``read_frame()`` (headless framebuffer).
+
+``mode="reference"`` issues the reference's 13 launches one by one through ocl_begin/ocl_param/ocl_end with the
+argument lists of the call sites, including the blocking 4-byte readback of idbuf_size (:298).
+``mode="fused"`` issues the same frame through ``svo_frame_fused`` (no host readback); results are identical.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import ocl
+
+HOLE = 0xFFFFFF00
+f32 = np.float32
+
+# globals of src/main.cpp:17-18,49-50 / src/raycast.h
+WINDOW_WIDTH_MAX = 2048
+WINDOW_HEIGHT_MAX = 1080
+OCTREE_DEPTH = 11
+
+
+class State:
+    pass
+
+
+S = State()
+S.ready = False
+
+
+def rotation_matrix(rot):
+    """matrix44 m; m.rotate_z(rot.z); m.rotate_x(rot.x); m.rotate_y(rot.y)  (src/raycast.h:121-124,
+    ext/mathlib/_matrix44.h:529-577), single precision."""
+    m = np.eye(4, dtype=np.float32)
+    for axis, (a, b) in ((2, (0, 1)), (0, (1, 2)), (1, (0, 2))):
+        ang = float(f32(rot[axis]))
+        c, s = f32(math.cos(ang)), f32(math.sin(ang))
+        for i in range(4):
+            va, vb = m[i, a], m[i, b]
+            if axis == 1:       # rotate_y: m[i][0] = mi0*c + mi2*s ; m[i][2] = mi0*-s + mi2*c
+                m[i, a] = f32(va * c) + f32(vb * s)
+                m[i, b] = f32(va * -s) + f32(vb * c)
+            else:               # rotate_x / rotate_z: first = a*c + b*-s ; second = a*s + b*c
+                m[i, a] = f32(va * c) + f32(vb * -s)
+                m[i, b] = f32(va * s) + f32(vb * c)
+    return m
+
+
+def wrap_pos(pos, depth=None):
+    """src/raycast.h:136-145."""
+    depth = OCTREE_DEPTH if depth is None else depth
+    dim2 = f32((1 << depth) * 2)
+    p = np.asarray(pos, dtype=np.float32) * f32(16.0)
+    for k in range(3):
+        while p[k] < 0:
+            p[k] = p[k] + dim2
+        while p[k] >= dim2:
+            p[k] = p[k] - dim2
+    return (p / f32(16.0)).astype(np.float32)
+
+
+def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth=11, device=0, mode="fused"):
+    """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree)."""
+    global WINDOW_WIDTH_MAX, WINDOW_HEIGHT_MAX, OCTREE_DEPTH
+    if max_w:
+        WINDOW_WIDTH_MAX = max_w
+    if max_h:
+        WINDOW_HEIGHT_MAX = max_h
+    OCTREE_DEPTH = depth
+    ocl.ocl_init(device)
+    ocl.set_octree_depth(depth)
+    octree_words = np.ascontiguousarray(octree_words, dtype=np.uint32)
+    size = WINDOW_WIDTH_MAX * WINDOW_HEIGHT_MAX
+    S.mem_octree = ocl.ocl_malloc(octree_words.nbytes, octree_words)             # :68
+    S.mem_bvh_nodes = None                                                         # never allocated (:71)
+    S.mem_bvh_childs = None                                                        # never allocated (:74)
+    S.mem_stack = None            # the reference allocates 128 MiB no kernel ever touches (:77); not reproduced
+    S.mem_backbuffer = ocl.ocl_malloc(size * 16 * 4)                               # :82
+    S.mem_screenbuffer = ocl.ocl_malloc(size * 4 * 4)                              # :85
+    S.mem_screenbuffer_tex = ocl.ocl_malloc(size * 4)                              # PBO stand-in (:88-89)
+    S.mem_x = S.mem_y = None                                                       # dead kernel arguments (:170-171)
+    S.mem_z = ocl.ocl_malloc(4 * size)                                             # :172 (only ever memset)
+    S.mem_idbuffer = ocl.ocl_malloc((size + (WINDOW_WIDTH_MAX // 16) * (WINDOW_HEIGHT_MAX // 16)) * 4 + 1024)  # :268-270
+    S.octree_root_normal = int(octree_root_normal)
+    S.frame = -1
+    S.pos = np.array([1, 50, 1], dtype=np.float32)                                 # :113
+    S.rot = np.array([0.0001, 0, 0], dtype=np.float32)                             # :114
+    S.mode = mode
+    S.idbuf_size = 0
+    S.k = {}
+    S.ready = True
+
+
+def _kernel(name):
+    if name not in S.k:
+        S.k[name] = ocl.ocl_get_kernel(name)       # function-local statics in the reference
+    return S.k[name]
+
+
+def set_camera(pos, rot):
+    S.pos = np.asarray(pos, dtype=np.float32).copy()
+    S.rot = np.asarray(rot, dtype=np.float32).copy()
+
+
+def tile_origin(frame, res_x, res_y):
+    """src/raycast.h:363-364: rotating 8x4 tile refresh schedule."""
+    return (res_x // 8) * (frame & 7), (res_y // 4) * ((frame >> 3) & 3)
+
+
+def raycast_draw(res_x, res_y):
+    """One frame; returns the camera actually used (after the wrap of :136-145)."""
+    S.frame += 1
+    frame = S.frame
+    fovx = fovy = f32(1.0)                                                         # :109-110
+    m = rotation_matrix(S.rot)
+    S.pos = wrap_pos(S.pos)
+    pos = S.pos
+    v0 = np.array([pos[0], pos[1], pos[2], 1.0], dtype=np.float32)                 # :159
+    rows = [m[i, :].copy() for i in range(3)]                                      # :160-162
+    cols = [m[:, i].copy() for i in range(3)]                                      # :322-325
+    S.last_camera = dict(pos=pos.copy(), v0=v0, rows=rows, cols=cols)
+    if S.mode == "fused":
+        p = ocl.FrameParams()
+        p.res_x, p.res_y, p.frame = res_x, res_y, frame
+        p.v0[:] = v0.tolist()
+        for i in range(3):
+            p.rows[i][:] = rows[i].tolist()
+            p.cols[i][:] = cols[i].tolist()
+        p.fovx, p.fovy = fovx, fovy
+        ocl.ocl_begin_all_kernels()
+        ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal,
+                        S.mem_screenbuffer_tex, p)
+        ocl.ocl_end_all_kernels()
+        return S.last_camera
+
+    i32, u32, fl = C.c_int, C.c_uint32, C.c_float
+    n = res_x * res_y
+    size_col, size_xyz = n * 4, n * 16                                             # :106-107
+    ocl.ocl_begin_all_kernels()                                                    # :147
+    if frame < 2:
+        ocl.ocl_memset(S.mem_screenbuffer, 0, HOLE, n * 4 * 4)                     # :150-154
+    ocl.ocl_memset(S.mem_screenbuffer, 0, HOLE, n * 4)                             # :157
+    ocl.ocl_memset(S.mem_z, 0, 0xFFFFFFFF, n * 4)                                  # :173
+    for i in range(2):                                                             # :177-198
+        ocl.ocl_begin(_kernel("raycast_proj"), res_x, res_y, 16, 16)
+        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_x, S.mem_y, S.mem_z):
+            ocl.ocl_param(a)
+        for a in (res_x, res_y, frame, (i + 1) * n):
+            ocl.ocl_param(i32(a))
+        for a in (v0, rows[0], rows[1], rows[2]):
+            ocl.ocl_param(a)
+        ocl.ocl_end()
+    for name in ("raycast_counthole", "raycast_sumids", "raycast_writeids"):       # :272-315
+        if name == "raycast_sumids":
+            ocl.ocl_begin(_kernel(name), 1, 1, 1, 1)
+        else:
+            ocl.ocl_begin(_kernel(name), res_x // 16, res_y // 16, 16, 16)
+        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer):
+            ocl.ocl_param(a)
+        for a in (res_x, res_y, frame):
+            ocl.ocl_param(i32(a))
+        ocl.ocl_end()
+        if name == "raycast_sumids":
+            out = np.zeros(1, dtype=np.int32)
+            ocl.ocl_copy_to_host(out, S.mem_idbuffer, 4)                           # :298 blocking readback
+            S.idbuf_size = int(out[0])
+    dead = (0.0, 0.0, 0.0, 0.0)         # a_cam, a_origin, a_dx, a_dy: unused by every kernel
+    if S.idbuf_size > 0:                                                           # :332-359
+        ocl.ocl_begin(_kernel("raycast_holes"), S.idbuf_size, 1, 256, 1)
+        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree, S.mem_bvh_nodes, S.mem_bvh_childs, S.mem_stack,
+                  S.mem_idbuffer):
+            ocl.ocl_param(a)
+        ocl.ocl_param(u32(S.octree_root_normal))
+        for a in (res_x, res_y, frame, S.idbuf_size):
+            ocl.ocl_param(i32(a))
+        for a in (dead, dead, dead, dead, v0, cols[0], cols[1], cols[2]):
+            ocl.ocl_param(a)
+        ocl.ocl_param(fl(fovx)); ocl.ocl_param(fl(fovy))
+        ocl.ocl_end()
+    add_x, add_y = tile_origin(frame, res_x, res_y)                                # :361-387
+    ocl.ocl_begin(_kernel("raycast_fine_2"), res_x // 8, res_y // 4, 16, 16)
+    for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree):
+        ocl.ocl_param(a)
+    ocl.ocl_param(u32(S.octree_root_normal))
+    for a in (res_x, res_y, frame, add_x, add_y):
+        ocl.ocl_param(i32(a))
+    for a in (dead, dead, dead, dead, v0, cols[0], cols[1], cols[2]):
+        ocl.ocl_param(a)
+    ocl.ocl_param(fl(fovx)); ocl.ocl_param(fl(fovy))
+    ocl.ocl_end()
+    target = 2                                                                     # :395
+    ocl.ocl_memcpy(S.mem_screenbuffer, size_col * target, S.mem_screenbuffer, 0, size_col)   # :396-399
+    ocl.ocl_memcpy(S.mem_backbuffer, size_xyz * target, S.mem_backbuffer, 0, size_xyz)       # :401-404
+    ocl.ocl_begin(_kernel("raycast_fillhole2"), res_x, res_y, 16, 16)              # :414-421
+    for a in (S.mem_screenbuffer, S.mem_backbuffer):
+        ocl.ocl_param(a)
+    for a in (res_x, res_y, frame):
+        ocl.ocl_param(i32(a))
+    ocl.ocl_end()
+    ocl.ocl_begin(_kernel("raycast_colorize"), res_x, res_y, 16, 16)               # :430-436
+    ocl.ocl_param(S.mem_screenbuffer); ocl.ocl_param(S.mem_screenbuffer_tex)
+    ocl.ocl_param(i32(res_x)); ocl.ocl_param(i32(res_y))
+    ocl.ocl_end()
+    ocl.ocl_end_all_kernels()                                                      # :438
+    return S.last_camera
+
+
+def idbuf_size():
+    return ocl.frame_idbuf_size() if S.mode == "fused" else S.idbuf_size
+
+
+def read_frame(res_x, res_y):
+    """Headless framebuffer: the colorized 0x00RRGGBB image the reference blits through the PBO (:449-455)."""
+    return S.mem_screenbuffer_tex.to_numpy(np.uint32, res_x * res_y).reshape(res_y, res_x)
+
+
+def read_buffers(res_x, res_y):
+    """(screen[4N], back[16N] float32, idbuf) of the current resolution, for parity checks."""
+    n = res_x * res_y
+    nb = (res_x // 16) * (res_y // 16)
+    screen = S.mem_screenbuffer.to_numpy(np.uint32, 4 * n)
+    back = S.mem_backbuffer.to_numpy(np.float32, 16 * n)
+    idb = S.mem_idbuffer.to_numpy(np.uint32, 2 * nb + n)
+    return screen, back, idb
+
+
+def raycast_exit():
+    """src/raycast.h:511-517."""
+    if not S.ready:
+        return
+    for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_z", "mem_idbuffer"):
+        m = getattr(S, name, None)
+        if m is not None:
+            m.free()
+            setattr(S, name, None)
+    ocl.ocl_exit()
+    S.ready = False
