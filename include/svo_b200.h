@@ -71,6 +71,21 @@ void svo_end_all_kernels(void);                                          /* ocl_
 size_t svo_round_up(int group_size, int global_size);                    /* ocl_round_up() src/ocl.h:188-198 */
 uint64_t svo_launch_count(void);                                         /* CUDA kernels launched by this library so far */
 
+/* ---- timing (extension; the reference's profiler is dead code, src/raycast.h:164-166,476-492) ------- */
+/* CUDA events on the context's stream. slot 0..15. elapsed waits for event b. */
+void   svo_event_record(int slot);
+float  svo_event_elapsed_ms(int slot_a, int slot_b);
+/* per-kernel device time: when enabled every launch is bracketed by events (slower; for breakdowns only).
+ * svo_profile_get(name): accumulated milliseconds and launch count of the CUDA kernel `name` since reset. */
+void   svo_profile_enable(int on);
+void   svo_profile_reset(void);
+int    svo_profile_get(const char *cuda_kernel_name, double *total_ms, uint64_t *launches);
+int    svo_profile_names(char *buf, size_t bufsize);        /* newline-separated kernel names seen so far */
+/* page-locked host memory for the headless framebuffer readback */
+void  *svo_host_alloc(size_t bytes);
+void   svo_host_free(void *p);
+void   svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, size_t srcofs);   /* ordered on the stream; svo_end_all_kernels() waits */
+
 /* ---- fused frame (B200-native fast path; same results as the 13-launch sequence of
  *      raycast_draw, src/raycast.h:147-438, without the mid-frame host readback) ------------------ */
 typedef struct svo_frame_params {

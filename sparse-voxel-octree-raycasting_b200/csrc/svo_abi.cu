@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 using namespace svo;
@@ -61,8 +63,14 @@ struct svo_ctx_s {
     uint32_t *snap = nullptr;               // fillhole2 snapshot
     size_t snap_words = 0;
     uint64_t launches = 0;
-    int last_idbuf_words = 0;               // 2*B of the last fused frame (where idb[0] holds the total)
-    svo_mem_t last_idbuf = nullptr;
+    svo_mem_t last_idbuf = nullptr;         // id buffer of the last fused frame (word 0 = idbuf_size)
+    cudaEvent_t events[16] = {};
+    // per-kernel profiling (svo_profile_*)
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    std::map<std::string, std::pair<double, uint64_t>> prof_acc;
 };
 
 static svo_ctx_t g_ctx = nullptr;           // current context (the reference's globals, src/ocl.h:8-16)
@@ -106,6 +114,9 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamSynchronize(c->stream);
     if (c->key) cudaFree(c->key);
     if (c->snap) cudaFree(c->snap);
+    for (auto &e : c->events) if (e) cudaEventDestroy(e);
+    for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto &e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     if (g_ctx == c) g_ctx = nullptr;
     delete c;
@@ -186,6 +197,77 @@ extern "C" void svo_copy_to_device(svo_mem_t dst, size_t dstofs, const void *src
     CU_CHECK(cudaStreamSynchronize(c->stream));
 }
 
+extern "C" void *svo_host_alloc(size_t bytes)
+{
+    need_ctx();
+    void *p = nullptr;
+    CU_CHECK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    return p;
+}
+extern "C" void svo_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, size_t srcofs)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!src || srcofs + size > src->bytes) { svo_fail(-104, "svo_copy_to_host_async out of range"); return; }
+    CU_CHECK(cudaMemcpyAsync(dst, (const char *)src->dptr + srcofs, size, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// ---- timing -----------------------------------------------------------------------------------------
+extern "C" void svo_event_record(int slot)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || slot < 0 || slot >= 16) return;
+    if (!c->events[slot]) CU_CHECK(cudaEventCreate(&c->events[slot]));
+    CU_CHECK(cudaEventRecord(c->events[slot], c->stream));
+}
+extern "C" float svo_event_elapsed_ms(int a, int b)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || a < 0 || b < 0 || a >= 16 || b >= 16 || !c->events[a] || !c->events[b]) return -1.f;
+    float ms = -1.f;
+    CU_CHECK(cudaEventSynchronize(c->events[b]));
+    CU_CHECK(cudaEventElapsedTime(&ms, c->events[a], c->events[b]));
+    return ms;
+}
+static void prof_flush(svo_ctx_t c)
+{
+    if (c->prof_pending.empty()) return;
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_pending) {
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+        auto &acc = c->prof_acc[r.name];
+        acc.first += ms; acc.second += 1;
+        c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_pending.clear();
+}
+extern "C" void svo_profile_enable(int on) { svo_ctx_t c = need_ctx(); if (c) { prof_flush(c); c->profiling = on != 0; } }
+extern "C" void svo_profile_reset(void) { svo_ctx_t c = need_ctx(); if (c) { prof_flush(c); c->prof_acc.clear(); } }
+extern "C" int svo_profile_get(const char *name, double *total_ms, uint64_t *launches)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || !name) return -1;
+    prof_flush(c);
+    auto it = c->prof_acc.find(name);
+    if (it == c->prof_acc.end()) { if (total_ms) *total_ms = 0; if (launches) *launches = 0; return 1; }
+    if (total_ms) *total_ms = it->second.first;
+    if (launches) *launches = it->second.second;
+    return 0;
+}
+extern "C" int svo_profile_names(char *buf, size_t bufsize)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || !buf || !bufsize) return -1;
+    prof_flush(c);
+    std::string all;
+    for (auto &kv : c->prof_acc) { all += kv.first; all += "\n"; }
+    snprintf(buf, bufsize, "%s", all.c_str());
+    return (int)c->prof_acc.size();
+}
+
 extern "C" size_t svo_round_up(int group_size, int global_size)       // src/ocl.h:188-198
 {
     const int r = global_size % group_size;
@@ -205,11 +287,28 @@ static inline int bw_grid(svo_ctx_t c, size_t items, int block = 256, int per_sm
     return g ? (int)g : 1;
 }
 
-#define LAUNCHED(c)                                   \
-    do {                                              \
-        (c)->launches++;                              \
-        CU_CHECK(cudaGetLastError());                 \
-    } while (0)
+static cudaEvent_t prof_event(svo_ctx_t c)
+{
+    cudaEvent_t e;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    CU_CHECK(cudaEventCreate(&e));
+    return e;
+}
+// brackets one kernel launch: counts it, checks it, and (profiling only) times it with events on the stream
+struct LaunchScope {
+    svo_ctx_t c; const char *name; cudaEvent_t a = nullptr;
+    LaunchScope(svo_ctx_t ctx, const char *n) : c(ctx), name(n)
+    {
+        if (c->profiling) { a = prof_event(c); CU_CHECK(cudaEventRecord(a, c->stream)); }
+    }
+    ~LaunchScope()
+    {
+        c->launches++;
+        CU_CHECK(cudaGetLastError());
+        if (a) { cudaEvent_t b = prof_event(c); CU_CHECK(cudaEventRecord(b, c->stream)); c->prof_pending.push_back({name, a, b}); }
+    }
+};
+#define LAUNCH(c, name) LaunchScope _ls((c), (name))
 
 static void ensure_key(svo_ctx_t c, size_t pixels)
 {
@@ -231,15 +330,13 @@ static void ensure_snap(svo_ctx_t c, size_t words)
 static void do_memset(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, uint32_t val, uint32_t nwords)
 {
     if (!nwords) return;
-    k_memset<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, val, nwords);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_memset"); k_memset<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, val, nwords); }
 }
 
 static void do_memcpy(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, const uint32_t *src, uint32_t srcofs, uint32_t nwords)
 {
     if (!nwords) return;
-    k_memcpy<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, src, srcofs, nwords);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_memcpy"); k_memcpy<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, src, srcofs, nwords); }
 }
 
 static ProjCam make_proj_cam(const float *m0, const float *mx, const float *my, const float *mz)
@@ -255,34 +352,29 @@ static void do_proj_scatter(svo_ctx_t c, uint32_t *screen, float *back, int res_
 {
     const size_t n = (size_t)res_x * res_y;
     ensure_key(c, n);
-    k_proj_scatter<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, ofs_add, cam);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_proj_scatter"); k_proj_scatter<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, ofs_add, cam); }
 }
 static void do_proj_resolve(svo_ctx_t c, uint32_t *screen, float *back, int res_x, int res_y, const ProjCam &cam)
 {
     const size_t n = (size_t)res_x * res_y;
-    k_proj_resolve<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, cam);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_proj_resolve"); k_proj_resolve<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, cam); }
 }
 
 static void do_counthole(svo_ctx_t c, const uint32_t *screen, uint32_t *idb, int res_x, int res_y)
 {
     const int nb = (res_x / 16) * (res_y / 16);
     if (!nb) return;
-    k_counthole<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_counthole"); k_counthole<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y); }
 }
 static void do_sumids(svo_ctx_t c, uint32_t *idb, int res_x, int res_y)
 {
-    k_sumids<<<1, 1024, 0, c->stream>>>(idb, (res_x / 16) * (res_y / 16));
-    LAUNCHED(c);
+    { LAUNCH(c, "k_sumids"); k_sumids<<<1, 1024, 0, c->stream>>>(idb, (res_x / 16) * (res_y / 16)); }
 }
 static void do_writeids(svo_ctx_t c, const uint32_t *screen, uint32_t *idb, int res_x, int res_y)
 {
     const int nb = (res_x / 16) * (res_y / 16);
     if (!nb) return;
-    k_writeids<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_writeids"); k_writeids<<<(nb + 7) / 8, 256, 0, c->stream>>>(screen, idb, res_x, res_y); }
 }
 
 // size_ptr != nullptr: idbuf_size is read on the device and the grid is a fixed persistent one
@@ -295,11 +387,11 @@ static void do_holes(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t 
         if (idbuf_size <= 0) return;
         grid = (idbuf_size + kRayBlock - 1) / kRayBlock;
     }
+    LAUNCH(c, "k_raycast_holes");
     if (c->depth == 11)
         k_raycast_holes<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, idb, size_ptr, root, res_x, res_y, idbuf_size, cam);
     else
         k_raycast_holes<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, idb, size_ptr, root, res_x, res_y, idbuf_size, cam);
-    LAUNCHED(c);
 }
 
 static void do_fine_2(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t *oct, uint32_t root, int res_x, int res_y,
@@ -307,11 +399,11 @@ static void do_fine_2(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t
 {
     if (gx <= 0 || gy <= 0) return;
     dim3 grid((gx + 31) / 32, (gy + 7) / 8);
+    LAUNCH(c, "k_raycast_fine_2");
     if (c->depth == 11)
         k_raycast_fine_2<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
     else
         k_raycast_fine_2<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
-    LAUNCHED(c);
 }
 
 // snapshot source: `snap_src` if the caller knows a buffer with the same content (fused frame: the cache copy),
@@ -327,16 +419,14 @@ static void do_fillhole2(svo_ctx_t c, uint32_t *screen, const uint32_t *snap_src
         do_memcpy(c, c->snap, 0, screen, 0, (uint32_t)words);
         snap = c->snap;
     }
-    k_fillhole2<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, snap, res_x, res_y);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_fillhole2"); k_fillhole2<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, snap, res_x, res_y); }
 }
 
 static void do_colorize(svo_ctx_t c, const uint32_t *screen, uint32_t *tex, int w, int h)
 {
     const size_t n = (size_t)w * h;
     if (!n) return;
-    k_colorize<<<bw_grid(c, (n + 3) / 4), 256, 0, c->stream>>>(screen, tex, (int)n);
-    LAUNCHED(c);
+    { LAUNCH(c, "k_colorize"); k_colorize<<<bw_grid(c, (n + 3) / 4), 256, 0, c->stream>>>(screen, tex, (int)n); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,13 +509,12 @@ extern "C" svo_kernel_t svo_get_kernel(const char *name)
 struct ArgSlot { size_t size; unsigned char bytes[16]; };
 static int g_narg = 0;
 static ArgSlot g_args[32];
-static size_t g_global[2], g_local[2];
+static size_t g_global[2];
 static svo_kernel_t g_current = nullptr;
 
 extern "C" void svo_begin(svo_kernel_t *kernel, int globalx, int globaly, int localx, int localy)
 {
     g_narg = 0;
-    g_local[0] = localx; g_local[1] = localy;
     g_global[0] = svo_round_up(localx, globalx);
     g_global[1] = svo_round_up(localy, globaly);
     g_current = kernel ? *kernel : nullptr;

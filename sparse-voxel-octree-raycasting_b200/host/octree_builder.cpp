@@ -171,7 +171,8 @@ struct TreeEmitter {
                 minidx = std::min(minidx, b.minidx);
             }
         }
-        const uint32_t col = v.rgba[minidx];
+        // the root is the pre-pushed zero node (src/raycast.h:15-17): set_voxel never gives it a colour
+        const uint32_t col = d == 0 ? 0u : v.rgba[minidx];
         for (int j = 0; j < 8; ++j) out[normal_ofs + j] = child[j];
         out[normal_ofs + 8] = col; out[normal_ofs + 9] = col;                               // :280-281
         normal_ofs += 10;

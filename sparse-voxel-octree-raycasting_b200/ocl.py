@@ -67,6 +67,16 @@ _svo_launch_count = _sig("svo_launch_count", C.c_uint64)
 _svo_frame_fused = _sig("svo_frame_fused", None, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(FrameParams))
 _svo_frame_idbuf_size = _sig("svo_frame_idbuf_size", _i)
 
+_svo_event_record = _sig("svo_event_record", None, _i)
+_svo_event_elapsed_ms = _sig("svo_event_elapsed_ms", C.c_float, _i, _i)
+_svo_profile_enable = _sig("svo_profile_enable", None, _i)
+_svo_profile_reset = _sig("svo_profile_reset", None)
+_svo_profile_get = _sig("svo_profile_get", _i, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64))
+_svo_profile_names = _sig("svo_profile_names", _i, C.c_char_p, _sz)
+_svo_host_alloc = _sig("svo_host_alloc", _vp, _sz)
+_svo_host_free = _sig("svo_host_free", None, _vp)
+_svo_copy_to_host_async = _sig("svo_copy_to_host_async", None, _vp, _vp, _sz, _sz)
+
 _raise_errors = False
 
 
@@ -231,3 +241,46 @@ def frame_fused(screen, back, idbuf, octree, root, tex, params):
 
 def frame_idbuf_size():
     return int(_svo_frame_idbuf_size())
+
+
+# ---- timing / profiling / pinned host memory (extensions of include/svo_b200.h) ----------------------------------
+def event_record(slot):
+    _svo_event_record(slot)
+
+
+def event_elapsed_ms(a, b):
+    return float(_svo_event_elapsed_ms(a, b))
+
+
+def profile_enable(on):
+    _svo_profile_enable(1 if on else 0)
+
+
+def profile_reset():
+    _svo_profile_reset()
+
+
+def profile_all():
+    """{cuda kernel name: (total ms, launches)} since the last reset."""
+    buf = C.create_string_buffer(4096)
+    _svo_profile_names(buf, 4096)
+    out = {}
+    for name in buf.value.decode().split():
+        ms, cnt = C.c_double(), C.c_uint64()
+        _svo_profile_get(name.encode(), C.byref(ms), C.byref(cnt))
+        out[name] = (ms.value, cnt.value)
+    return out
+
+
+def host_alloc(nbytes):
+    """Page-locked host buffer as a writable memoryview-compatible ctypes array."""
+    p = _svo_host_alloc(nbytes)
+    _check()
+    if not p:
+        raise MemoryError("svo_host_alloc failed")
+    return (C.c_uint8 * nbytes).from_address(p)
+
+
+def copy_to_host_async(dst, src, size, srcofs=0):
+    _svo_copy_to_host_async(C.addressof(dst), src.handle, size, srcofs)
+    _check()

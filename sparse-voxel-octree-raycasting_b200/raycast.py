@@ -210,6 +210,60 @@ def raycast_draw(res_x, res_y):
     return S.last_camera
 
 
+def prepare_params(res_x, res_y, frame):
+    """The per-frame camera block of the fused path (struct svo_frame_params) for the camera set with set_camera()."""
+    m = rotation_matrix(S.rot)
+    pos = wrap_pos(S.pos)
+    p = ocl.FrameParams()
+    p.res_x, p.res_y, p.frame = res_x, res_y, frame
+    p.v0[:] = [float(pos[0]), float(pos[1]), float(pos[2]), 1.0]
+    for i in range(3):
+        p.rows[i][:] = m[i, :].tolist()
+        p.cols[i][:] = m[:, i].tolist()
+    p.fovx = p.fovy = 1.0
+    return p
+
+
+def draw_prepared(p, sync=True):
+    """raycast_draw() of the fused path with a camera block prepared in advance (keeps Python out of the frame loop)."""
+    S.frame = p.frame
+    ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal,
+                    S.mem_screenbuffer_tex, p)
+    if sync:
+        ocl.ocl_end_all_kernels()
+
+
+def reset_frames():
+    S.frame = -1
+
+
+def full_raycast_ms(res_x, res_y, repeats=5):
+    """Device time (ms, median) of raycast_fine_2 over the whole screen for the camera set with set_camera()."""
+    m = rotation_matrix(S.rot)
+    pos = wrap_pos(S.pos)
+    v0 = np.array([pos[0], pos[1], pos[2], 1.0], dtype=np.float32)
+    cols = [m[:, i].copy() for i in range(3)]
+    dead = (0.0, 0.0, 0.0, 0.0)
+    times = []
+    for r in range(repeats + 2):
+        ocl.event_record(2)
+        ocl.ocl_begin(_kernel("raycast_fine_2"), res_x, res_y, 16, 16)
+        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree):
+            ocl.ocl_param(a)
+        ocl.ocl_param(C.c_uint32(S.octree_root_normal))
+        for a in (res_x, res_y, 0, 0, 0):
+            ocl.ocl_param(C.c_int(a))
+        for a in (dead, dead, dead, dead, v0, cols[0], cols[1], cols[2]):
+            ocl.ocl_param(a)
+        ocl.ocl_param(C.c_float(1.0)); ocl.ocl_param(C.c_float(1.0))
+        ocl.ocl_end()
+        ocl.event_record(3)
+        ms = ocl.event_elapsed_ms(2, 3)
+        if r >= 2:
+            times.append(ms)
+    return float(np.median(times))
+
+
 def idbuf_size():
     return ocl.frame_idbuf_size() if S.mode == "fused" else S.idbuf_size
 
