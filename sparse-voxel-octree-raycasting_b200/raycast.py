@@ -85,7 +85,9 @@ def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth
     S.mem_screenbuffer_tex = ocl.ocl_malloc(size * 4)                              # PBO stand-in (:88-89)
     S.mem_x = S.mem_y = None                                                       # dead kernel arguments (:170-171)
     S.mem_z = ocl.ocl_malloc(4 * size)                                             # :172 (only ever memset)
-    S.mem_idbuffer = ocl.ocl_malloc((size + (WINDOW_WIDTH_MAX // 16) * (WINDOW_HEIGHT_MAX // 16)) * 4 + 1024)  # :268-270
+    # :268-270 allocates MAXPIX + MAXB words, but counts + offsets + ids need N + 2B: the reference overruns by B words
+    # when the window is at its maximum size.  Allocated N + 2B here.
+    S.mem_idbuffer = ocl.ocl_malloc((size + 2 * (WINDOW_WIDTH_MAX // 16) * (WINDOW_HEIGHT_MAX // 16)) * 4)
     S.octree_root_normal = int(octree_root_normal)
     S.frame = -1
     S.pos = np.array([1, 50, 1], dtype=np.float32)                                 # :113
