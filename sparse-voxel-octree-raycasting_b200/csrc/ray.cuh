@@ -91,8 +91,8 @@ __device__ __forceinline__ uint32_t fetch_color(const uint32_t *__restrict__ oct
 
 // One primary ray for pixel (idx, idy): ray set-up of raycast_holes :639-663 / raycast_fine_2 :883-908,
 // CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
-// `stack` points at this thread's column of the shared [D+1][kRayBlock] array.
-template <int D>
+// `stack` points at this thread's column of the shared [D+1][STRIDE] array (STRIDE = threads per CTA).
+template <int D, int STRIDE = kRayBlock>
 __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
                                             int idx, int idy, const RayCam &c, uint32_t *stack)
@@ -137,7 +137,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
             before = tmp;
             if (rekursion <= lod) break;
             --rekursion;
-            stack[rekursion * kRayBlock] = nodeid;
+            stack[rekursion * STRIDE] = nodeid;
             continue;
         }
         const float mx = (float)((cx + 1) << rekursion) - px;
@@ -160,8 +160,8 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
         rekursion = 32 - __clz(x0r);                               // rekursion_new + 1
         if (rekursion >= D) { nodeid = before = root; }
         else {
-            nodeid = stack[rekursion * kRayBlock];
-            before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * kRayBlock];
+            nodeid = stack[rekursion * STRIDE];
+            before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
         }
         if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }
     } while (!(x0ry & (2 * kDepthAnd + 2)) && --guard);
@@ -170,7 +170,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     if (sign_xyz & 2) py = (float)kScaleMax - py;
     if (sign_xyz & 4) pz = (float)kScaleMax - pz;
 
-    const uint32_t before2 = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * kRayBlock];
+    const uint32_t before2 = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;

@@ -4,6 +4,7 @@
 #include "../../include/svo_b200.h"
 #include "ray.cuh"
 #include "warp.cuh"
+#include "fused.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -62,6 +63,9 @@ struct svo_ctx_s {
     size_t key_pixels = 0;
     uint32_t *snap = nullptr;               // fillhole2 snapshot
     size_t snap_words = 0;
+    FusedScratch fs = {nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
+    size_t fs_ctas = 0, fs_pixels = 0;
+    uint32_t epoch = 0;
     uint64_t launches = 0;
     svo_mem_t last_idbuf = nullptr;         // id buffer of the last fused frame (word 0 = idbuf_size)
     cudaEvent_t events[16] = {};
@@ -114,6 +118,9 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamSynchronize(c->stream);
     if (c->key) cudaFree(c->key);
     if (c->snap) cudaFree(c->snap);
+    if (c->fs.scan_state) cudaFree(c->fs.scan_state);
+    if (c->fs.counters) cudaFree(c->fs.counters);
+    if (c->fs.fixups) cudaFree(c->fs.fixups);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &e : c->prof_pool) cudaEventDestroy(e);
@@ -317,6 +324,25 @@ static void ensure_key(svo_ctx_t c, size_t pixels)
     CU_CHECK(cudaMalloc(&c->key, pixels * 8));
     CU_CHECK(cudaMemsetAsync(c->key, 0xff, pixels * 8, c->stream));
     c->key_pixels = pixels;
+}
+
+static void ensure_fused_scratch(svo_ctx_t c, size_t ctas, size_t pixels)
+{
+    if (!c->fs.counters) {
+        CU_CHECK(cudaMalloc(&c->fs.counters, 16));
+        CU_CHECK(cudaMemsetAsync(c->fs.counters, 0, 16, c->stream));
+    }
+    if (c->fs_ctas < ctas) {
+        if (c->fs.scan_state) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->fs.scan_state)); }
+        CU_CHECK(cudaMalloc(&c->fs.scan_state, ctas * 8));
+        CU_CHECK(cudaMemsetAsync(c->fs.scan_state, 0, ctas * 8, c->stream));
+        c->fs_ctas = ctas;
+    }
+    if (c->fs_pixels < pixels) {
+        if (c->fs.fixups) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->fs.fixups)); }
+        CU_CHECK(cudaMalloc(&c->fs.fixups, pixels * 8));
+        c->fs_pixels = pixels;
+    }
 }
 
 static void ensure_snap(svo_ctx_t c, size_t words)
@@ -660,26 +686,41 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     uint32_t *idb = (uint32_t *)idbuffer->dptr;
     const uint32_t *oct = (const uint32_t *)octree->dptr;
 
-    if (frame < 2) do_memset(c, screen, 0, kHole, n * 4);                     // :150-154
-    do_memset(c, screen, 0, kHole, n);                                        // :157
+    const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
+    ensure_key(c, n);
+    ensure_fused_scratch(c, ncta + 64, n);
+    const bool strips = (res_x % 16) || (res_y % 16);
+
+    if (frame < 2) do_memset(c, screen, n, kHole, n * 3);                      // :150-154 (buffer 0 is rewritten below)
     const ProjCam pc = make_proj_cam(p->v0, p->rows[0], p->rows[1], p->rows[2]);
-    do_proj_scatter(c, screen, back, res_x, res_y, (int)n, pc);               // :177-198, source buffer 1
-    do_proj_scatter(c, screen, back, res_x, res_y, (int)(2 * n), pc);         //           source buffer 2
-    do_proj_resolve(c, screen, back, res_x, res_y, pc);
-    do_counthole(c, screen, idb, res_x, res_y);                               // :272-282
-    do_sumids(c, idb, res_x, res_y);                                          // :287-296 (no readback)
-    do_writeids(c, screen, idb, res_x, res_y);                                // :305-315
+    {   // :177-198 both source buffers, ascending source offset = the reference's launch order
+        LAUNCH(c, "k_proj_scatter2");
+        k_proj_scatter2<<<bw_grid(c, 2 * (size_t)n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, c->fs.counters + 2, res_x, res_y, pc);
+    }
+    {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
+        LAUNCH(c, "k_resolve_gather");
+        c->epoch = (c->epoch + 1) & 0x3fffffffu;
+        if (c->epoch == 0) c->epoch = 1;
+        k_resolve_gather<<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(screen, back, c->key, idb, c->fs, c->epoch, res_x, res_y, pc);
+    }
     const RayCam rc = make_ray_cam(p->v0, p->cols[0], p->cols[1], p->cols[2], p->fovx, p->fovy);
-    do_holes(c, screen, back, oct, idb, idb, octree_root, res_x, res_y, 0, rc);   // :332-359, size = idb[0] on device
     const int add_x = (res_x / 8) * (frame & 7), add_y = (res_y / 4) * ((frame >> 3) & 3);   // :363-364
-    do_fine_2(c, screen, back, oct, octree_root, res_x, res_y, (int)svo_round_up(16, res_x / 8), (int)svo_round_up(16, res_y / 4),
-              add_x, add_y, rc);                                              // :365-386
-    do_memcpy(c, screen, 2 * n, screen, 0, n);                                // :394-405 (target = 2)
-    do_memcpy(c, (uint32_t *)back, 2 * n * 4, (const uint32_t *)back, 0, n * 4);
-    // :411-422; rows past the image are read from buffer 1 in the reference and from buffer 3 through the
-    // buffer-2 snapshot here: both are all-holes (nothing ever writes them), see DESIGN.md
-    do_fillhole2(c, screen, nullptr, res_x, res_y, screenbuffer->bytes / 4);
-    if (screenbuffer_tex) do_colorize(c, screen, (uint32_t *)screenbuffer_tex->dptr, res_x, res_y);   // :429-437
+    const int gx = (int)svo_round_up(16, res_x / 8), gy = (int)svo_round_up(16, res_y / 4);
+    {   // :332-387 hole rays (count on the device) + tile refresh rays, one list
+        LAUNCH(c, "k_rays");
+        const int grid = c->num_sms * 32;
+        if (c->depth == 11) k_rays<11><<<grid, kRaysBlock, 0, c->stream>>>(screen, back, oct, idb, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc);
+        else                k_rays<14><<<grid, kRaysBlock, 0, c->stream>>>(screen, back, oct, idb, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc);
+    }
+    {   // :394-437 cache copy (target 2) + gap filter + colorize
+        LAUNCH(c, "k_copy_fill_colorize");
+        k_copy_fill_colorize<<<bw_grid(c, (size_t)n / 4 + 4, 256, 8), 256, 0, c->stream>>>(
+            screen, back, screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr, c->fs, res_x, res_y, 2);
+    }
+    {
+        LAUNCH(c, "k_apply_fixups");
+        k_apply_fixups<<<32, 256, 0, c->stream>>>(screen, c->fs);
+    }
     c->last_idbuf = idbuffer;
 }
 

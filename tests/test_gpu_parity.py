@@ -182,18 +182,21 @@ def test_raycast_proj(svo, orc, world):
     ms.free(); mb.free()
 
 
-@pytest.mark.parametrize("mode", ["reference", "fused"])
-def test_frame_sequence(svo, orc, world, mode):
-    """40 frames of the full pipeline (covers a whole 32-tile refresh period): every buffer after every frame."""
+@pytest.mark.parametrize("mode,res,nframes", [("reference", (320, 192), 40), ("fused", (320, 192), 40),
+                                              ("fused", (200, 120), 8), ("reference", (200, 120), 4),
+                                              ("fused", (1920, 1024), 5)])
+def test_frame_sequence(svo, orc, world, mode, res, nframes):
+    """Frames of the full pipeline (40 covers a whole 32-tile refresh period): every buffer after every frame.
+    200x120 is not a multiple of the 16x16 hole-block size (right/bottom strips); 1920x1024 is the bench size."""
     octree, root = world
-    rx, ry = 320, 192
+    rx, ry = res
     n = rx * ry
-    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=4)
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4)
     rc = svo.raycast
     svo.ocl_exit()
     rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode=mode)
     try:
-        for f in range(40):
+        for f in range(nframes):
             pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
             O.draw(pos, rot)
             rc.set_camera(pos, rot)
