@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-frames", type=int, default=32)
+    ap.add_argument("--mode", default="fused", choices=["fused", "pingpong"],
+                    help="fused: every buffer as the reference leaves it (cache copy kept); pingpong: SVO_FRAME_PINGPONG, no cache copy")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
@@ -194,7 +196,7 @@ def main():
         dist.barrier()
     octree, root, stats = svo.scene.octree_init(path)          # .rle4 loader -> direct compact-octree builder
     rc, ocl = svo.raycast, svo.ocl
-    rc.raycast_init(octree, root, max_w=RES_X, max_h=RES_Y, device=local_rank, mode="fused")
+    rc.raycast_init(octree, root, max_w=RES_X, max_h=RES_Y, device=local_rank, mode=args.mode)
     n = RES_X * RES_Y
 
     def params(f):
@@ -292,7 +294,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
                 "config": {"workload": f"256-frame scripted flythrough, {RES_X}x{RES_Y}, full warping pipeline (reproject 2 buffers, 2x2 hole gather, "
                                        f"hole raycast, 8x4 tile refresh, cache copy, gap filter, colorize), scene: {scene_name}",
-                           "octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": "fused",
+                           "octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
                            "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} (one camera path per GPU, no communication)",
                            "l2_note": "working set per frame (2 x 20 B/pixel x 1.97 Mpixel + octree) exceeds nothing by construction: inputs change every frame; "
                                       "no L2 flush between frames (a frame reads what the previous frame wrote, as in the real pipeline)",

@@ -94,7 +94,14 @@ typedef struct svo_frame_params {
     float rows[3][4];            /* vx,vy,vz = rows of m    (raycast_proj)            src/raycast.h:160-162 */
     float cols[3][4];            /* vx,vy,vz = columns of m (ray kernels)             src/raycast.h:322-325 */
     float fovx, fovy;            /*                                                   src/raycast.h:109-110 */
+    int   flags;                 /* 0 or SVO_FRAME_PINGPONG */
 } svo_frame_params;
+
+/* SVO_FRAME_PINGPONG: do not copy the frame into cache buffer 2 (src/raycast.h:394-405); instead render alternately into
+ * buffer 0 and buffer 2 and reproject from the other one.  The slot rendered into (svo_frame_last_slot()) then holds
+ * exactly what the reference's cache buffer 2 holds after the frame, the id buffer and the colorized image are
+ * identical, and the small-gap filter's output exists in the colorized image only. */
+enum { SVO_FRAME_PINGPONG = 1 };
 
 /* One whole frame on buffers laid out as the reference's (4 colour + 4 coordinate buffers at stride
  * res_x*res_y, id buffer, octree, colorize target).  Asynchronous; svo_end_all_kernels() waits.
@@ -103,6 +110,8 @@ void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t idb
                      uint32_t octree_root, svo_mem_t screenbuffer_tex, const svo_frame_params *p);
 /* idbuf_size of the last fused frame (the value the reference reads back at src/raycast.h:298); blocking */
 int  svo_frame_idbuf_size(void);
+/* buffer index (0 or 2) the last fused frame was rendered into; always 0 without SVO_FRAME_PINGPONG */
+int  svo_frame_last_slot(void);
 
 #ifdef __cplusplus
 }

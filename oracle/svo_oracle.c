@@ -270,6 +270,8 @@ int orc_write_rle4(const char *path, int sx, int sy, int sz, size_t nslabs, cons
 /* Ray traversal (kernel/kernel.cl:32-214)                                               */
 /* ===================================================================================== */
 static uint64_t g_rays, g_iters, g_loads;
+static uint32_t *g_iter_buf = NULL;     /* optional per-pixel iteration counts (analysis of ray-length tails) */
+void orc_set_iter_buffer(uint32_t *buf) { g_iter_buf = buf; }
 void orc_stats_reset(void) { g_rays = g_iters = g_loads = 0; }
 void orc_stats(uint64_t *rays, uint64_t *iterations, uint64_t *octree_loads)
 {
@@ -441,6 +443,7 @@ static void shade_pixel(uint32_t *screen, float *back, const uint32_t *oct, uint
     back[ofs * 4 + 0] = r.px / 16.0f;
     back[ofs * 4 + 1] = r.py / 16.0f;
     back[ofs * 4 + 2] = r.pz / 16.0f;
+    if (g_iter_buf) g_iter_buf[ofs] = r.iters;
 #pragma omp atomic
     g_rays += 1;
 #pragma omp atomic

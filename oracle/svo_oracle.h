@@ -31,6 +31,7 @@ size_t   orc_num_nodes(void);
 int      orc_max_threads(void);
 
 /* instrumentation of the ray kernels: totals since the last orc_stats_reset() */
+void     orc_set_iter_buffer(uint32_t *per_pixel_iterations);   /* NULL = off */
 void     orc_stats_reset(void);
 void     orc_stats(uint64_t *rays, uint64_t *iterations, uint64_t *octree_loads);
 

@@ -1,15 +1,23 @@
-// fused.cuh -- the B200-native frame: the reference's 13-launch frame (src/raycast.h:147-438) as 5 launches with
-// no host round trip.  Every buffer ends the frame with exactly the content the reference sequence leaves.
+// fused.cuh -- the B200-native frame: the reference's 13-launch frame (src/raycast.h:147-438) as 6 launches on two
+// streams with no host round trip.
 //
-//   k_proj_scatter2        both reprojection launches (:177-198) -> 64-bit atomicMin keys (depth | source offset)
-//   k_resolve_gather       memset(:157) + depth-test resolve + raycast_counthole/sumids/writeids (:272-315) in one
-//                          pass over the keys: one thread per 2x2 cell, warp ballots per 16x16 block, decoupled
-//                          look-back scan across CTAs (ticket order = block order, so the id order is the reference's)
-//   k_rays                 raycast_holes (:332-359, count read on the device) + raycast_fine_2 tile refresh (:361-387)
-//                          as ONE ray list, 64-thread CTAs spread over all SMs
-//   k_copy_fill_colorize   cache copy (:394-405) + raycast_fillhole2 (:411-422) + raycast_colorize (:429-437) in one
-//                          pass; the few filled pixels are written to buffer 0 afterwards by
-//   k_apply_fixups         so that every fillhole2 read sees the pre-pass image (snapshot semantics).
+//   k_proj_scatter2   both reprojection launches (:177-198) -> 64-bit atomicMin keys (depth | source offset)
+//   k_resolve_gather  clear (:157) + depth-test resolve + raycast_counthole / sumids / writeids (:272-315) in one pass
+//                     over the keys: one thread per 2x2 cell, warp ballots per 16x16 block, decoupled look-back scan
+//                     across CTAs in ticket order (= block order, so the id order is the reference's); also lists the
+//                     hole pixels no ray will fill (input of the gap filter)
+//   k_rays_tile       raycast_fine_2 tile refresh (:361-387); independent of the reprojection, so it runs on a second
+//                     stream concurrently with the two kernels above
+//   k_rays_holes      raycast_holes (:332-359); idbuf_size is read on the device
+//   k_copy_colorize   cache copy (:394-405) + raycast_colorize (:429-437), pure streaming
+//   k_fill_list       raycast_fillhole2 (:411-422) on the listed hole pixels only, snapshot semantics
+//
+// Buffer roles are parameters (slot = buffer index in the reference's 4-buffer arrays):
+//   exact mode      sources = slots 1 and 2, destination = slot 0, copy target = slot 2: every buffer ends the frame
+//                   with exactly the content the reference sequence leaves;
+//   ping-pong mode  source = the slot the previous frame rendered into, destination = the other one of {0, 2}, no copy:
+//                   the destination slot holds what the reference's cache buffer 2 holds, the gap filter's output goes
+//                   to the colorized image only.
 #pragma once
 #include "warp.cuh"
 
@@ -17,64 +25,89 @@ namespace svo {
 
 struct FusedScratch {
     unsigned long long *scan_state;   // per CTA ticket: epoch<<34 | flag<<32 | value
-    unsigned int *counters;           // [0] ticket, [1] done, [2] fixup count
-    uint2 *fixups;                    // (offset, value) of pixels filled by the gap filter
+    unsigned int *counters;           // [0] ticket, [1] done, [2],[3] residual-hole counts (alternating frames)
+    uint32_t *resid;                  // pixel offsets of the hole pixels left for the gap filter
+    unsigned int *resid_count;        // this frame's counter (&counters[2 + parity])
 };
 
+struct Rect { int x0, y0, x1, y1; };  // tile-refresh rectangle [x0,x1) x [y0,y1) in pixels
+__device__ __forceinline__ bool in_rect(const Rect &r, int x, int y) { return x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1; }
+
 // ---------------------------------------------------------------------------------------------------------
+// Reprojection, fast path.  The reference evaluates the screen coordinate in double and truncates the single-rounded
+// float (kernel.cl:552-557).  Only the truncated integer is used, so the all-float value is good enough unless it lies
+// within its error bound of an integer; those (about 1 in 1000) take the exact double path.
+__device__ __forceinline__ bool proj_point_fast(const ProjCam &c, float pcx, float pcy, float pcz, int res_x, int res_y,
+                                                int &scrx, int &scry, float &phz)
+{
+    const float qx = pcx - c.m0x, qy = pcy - c.m0y, qz = pcz - c.m0z;
+    const float phx = qx * c.mxx + qy * c.mxy + qz * c.mxz;
+    const float phy = qx * c.myx + qy * c.myy + qz * c.myz;
+    phz = qx * c.mzx + qy * c.mzy + qz * c.mzz;
+    if (phz < 0.05f) return false;                      // == ((double)phz < 0.05): 0.05f is the smallest float above 0.05
+    const float hx = (float)res_x / 2.0f, hy = (float)res_y / 2.0f;
+    const float ax = phx * (float)res_y, ay = phy * (float)res_y;
+    const float qfx = ax / phz, qfy = ay / phz;
+    const float fx = qfx + hx, fy = qfy + hy;
+    const float tolx = (fabsf(fx) + fabsf(qfx) + 1.0f) * 1.1920929e-7f;
+    const float toly = (fabsf(fy) + fabsf(qfy) + 1.0f) * 1.1920929e-7f;
+    const bool okx = fabsf(fx - rintf(fx)) > tolx && fabsf(fx) < 1.0e6f;
+    const bool oky = fabsf(fy - rintf(fy)) > toly && fabsf(fy) < 1.0e6f;
+    if (okx) scrx = __float2int_rz(fx);
+    else scrx = f2i_trunc((float)(((double)ax + 0.0) / (double)phz + (double)hx - 0.0));
+    if (oky) scry = __float2int_rz(fy);
+    else scry = f2i_trunc((float)(((double)ay + 0.0) / (double)phz + (double)hy - 0.0));
+    return !(scrx >= res_x - 1 || scrx < 0 || scry >= res_y - 1 || scry < 0);
+}
+
+// sources: `nsrc` pixels starting at pixel offset `src0` (exact mode: buffers 1 and 2 = 2N pixels from N; ascending
+// offset is the launch order of the reference, which is what breaks depth ties)
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
-                unsigned int *__restrict__ fixup_count, int res_x, int res_y, ProjCam c)
+                unsigned int *__restrict__ next_resid_count, int res_x, int res_y, unsigned int src0, unsigned int nsrc, ProjCam c)
 {
-    const int n = res_x * res_y;
-    if (blockIdx.x == 0 && threadIdx.x == 0) fixup_count[0] = 0;      // re-arm the gap-filter fix-up list of this frame
-    // sources: buffer 1 then buffer 2, i.e. offsets n .. 3n-1; ascending offset = launch order of the reference
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 2 * n; q += gridDim.x * blockDim.x) {
-        const uint32_t srcofs = (uint32_t)(q + n);
+    // re-arm the NEXT frame's gap-filter counter (this frame's may already be in use by the concurrent tile rays)
+    if (blockIdx.x == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < nsrc; q += gridDim.x * blockDim.x) {
+        const uint32_t srcofs = q + src0;
         const uint32_t col = screen[srcofs];
         if (col == kHole) continue;
         const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4);
         int sx, sy; float phz;
-        if (!proj_point(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) { screen[srcofs] = kHole; continue; }
+        if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) { screen[srcofs] = kHole; continue; }
         atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// One pixel of the resolve: destination buffer 0 was (logically) just cleared to holes, so a candidate is
-// accepted iff its sz is below 0xffffff00 (kernel.cl:571 against an empty destination).
-__device__ __forceinline__ bool resolve_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
-                                              unsigned long long k, size_t p, const ProjCam &c, uint32_t &out_col)
-{
-    if (k != kKeyEmpty) {
-        const uint32_t sz = (uint32_t)(k >> 32), srcofs = (uint32_t)k;
-        if (sz < 0xffffff00u) {
-            const uint32_t col = screen[srcofs];
-            const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4);
-            const float qx = pc.x - c.m0x, qy = pc.y - c.m0y, qz = pc.z - c.m0z;
-            const float phz = qx * c.mzx + qy * c.mzy + qz * c.mzz;
-            out_col = sz + (col & 255u);
-            *reinterpret_cast<float4 *>(back + p * 4) = make_float4(pc.x, pc.y, pc.z, phz);
-            return true;
-        }
-    }
-    out_col = kHole;
-    return false;
-}
-
 constexpr int kGatherBlocksPerCta = 4;      // 16x16 screen blocks per 256-thread CTA (2 warps each)
 
+struct GatherArgs {
+    uint32_t *screen; float *back; unsigned long long *key; uint32_t *idb;
+    FusedScratch s; uint32_t epoch; int res_x, res_y;
+    unsigned int dst0;        // pixel offset of the destination slot
+    Rect tile; int skip_tile; // tile rays run concurrently: leave colour / xyz of the tile rectangle to them
+    ProjCam c;
+};
+
+// The destination was (logically) just cleared to holes, so a candidate is accepted iff its sz is below 0xffffff00
+// (kernel.cl:571 against an empty destination).
+__device__ __forceinline__ bool key_valid(unsigned long long k) { return k != kKeyEmpty && (uint32_t)(k >> 32) < 0xffffff00u; }
+
 __global__ void __launch_bounds__(256)
-k_resolve_gather(uint32_t *__restrict__ screen, float *__restrict__ back, unsigned long long *__restrict__ key,
-                 uint32_t *__restrict__ idb, FusedScratch s, uint32_t epoch, int res_x, int res_y, ProjCam c)
+k_resolve_gather(const GatherArgs a)
 {
     __shared__ unsigned int ticket_s;
     __shared__ uint32_t warp_cnt[8];
     __shared__ uint32_t cta_prefix_s;
+    __shared__ unsigned int resid_cta_s, resid_base_s;
+    const int res_x = a.res_x, res_y = a.res_y;
     const int nbx = res_x / 16, nby = res_y / 16, nblocks = nbx * nby;
     const int ncta = (nblocks + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) ticket_s = atomicAdd(&s.counters[0], 1u);
+    uint32_t *__restrict__ dscreen = a.screen + a.dst0;
+    float *__restrict__ dback = a.back + (size_t)a.dst0 * 4;
+    if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
     __syncthreads();
     const unsigned int ticket = ticket_s;
 
@@ -89,70 +122,132 @@ k_resolve_gather(uint32_t *__restrict__ screen, float *__restrict__ back, unsign
             if (i < n_right) { x = wx + i % (res_x - wx); y = i / (res_x - wx); }
             else { const int j = i - n_right; x = j % res_x; y = wy + j / res_x; }
             const size_t p = (size_t)y * res_x + x;
-            const unsigned long long k = key[p];
-            if (k != kKeyEmpty) key[p] = kKeyEmpty;
-            uint32_t col;
-            resolve_pixel(screen, back, k, p, c, col);
-            screen[p] = col;
+            const unsigned long long k = a.key[p];
+            if (k != kKeyEmpty) a.key[p] = kKeyEmpty;
+            const bool v = key_valid(k), inr = a.skip_tile && in_rect(a.tile, x, y);
+            if (v) {
+                const uint32_t srcofs = (uint32_t)k;
+                const uint32_t col = a.screen[srcofs];
+                const float4 pc = *reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4);
+                const float phz = (pc.x - a.c.m0x) * a.c.mzx + (pc.y - a.c.m0y) * a.c.mzy + (pc.z - a.c.m0z) * a.c.mzz;
+                if (inr) dback[p * 4 + 3] = phz;
+                else { dscreen[p] = (uint32_t)(k >> 32) + (col & 255u); *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz); }
+            } else if (!inr) {
+                dscreen[p] = kHole;
+                if (x > 1 && y > 1 && x < res_x - 1 && y < res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
+            }
         }
     } else {
         const int b = (int)ticket * kGatherBlocksPerCta + (warp >> 1);
         bool hole = false;
         int x = 0, y = 0;
+        bool valid[4] = {false, false, false, false}, inr[4] = {false, false, false, false};
+        size_t pp[2] = {0, 0};
         if (b < nblocks) {
             const int bx = b % nbx, by = b / nbx;
             x = bx * 16 + (lane & 7) * 2;
             y = by * 16 + ((warp & 1) * 4 + (lane >> 3)) * 2;
-            hole = true;
+            unsigned long long k[4];
+            const bool even = (res_x & 1) == 0;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t p = (size_t)(y + r) * res_x + x;
-                unsigned long long k0, k1;
-                if ((res_x & 1) == 0) {
-                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(key + p);
-                    k0 = kk.x; k1 = kk.y;
-                    if ((k0 & k1) != kKeyEmpty) *reinterpret_cast<ulonglong2 *>(key + p) = make_ulonglong2(kKeyEmpty, kKeyEmpty);
-                } else {
-                    k0 = key[p]; k1 = key[p + 1];
-                    key[p] = kKeyEmpty; key[p + 1] = kKeyEmpty;
-                }
-                uint32_t c0, c1;
-                const bool f0 = resolve_pixel(screen, back, k0, p, c, c0);
-                const bool f1 = resolve_pixel(screen, back, k1, p + 1, c, c1);
-                if ((res_x & 1) == 0) *reinterpret_cast<uint2 *>(screen + p) = make_uint2(c0, c1);
-                else { screen[p] = c0; screen[p + 1] = c1; }
-                hole = hole && !f0 && !f1;
+                pp[r] = p;
+                if (even) {
+                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(a.key + p);
+                    k[2 * r] = kk.x; k[2 * r + 1] = kk.y;
+                } else { k[2 * r] = a.key[p]; k[2 * r + 1] = a.key[p + 1]; }
             }
+            // all four gathers in flight before the first use
+            uint32_t col[4]; float4 pc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                valid[i] = key_valid(k[i]);
+                inr[i] = a.skip_tile && in_rect(a.tile, x + (i & 1), y + (i >> 1));
+                col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid[i]) {
+                    const uint32_t srcofs = (uint32_t)k[i];
+                    col[i] = a.screen[srcofs];
+                    pc[i] = *reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const size_t p = pp[r];
+                if ((k[2 * r] & k[2 * r + 1]) != kKeyEmpty) {
+                    if (even) *reinterpret_cast<ulonglong2 *>(a.key + p) = make_ulonglong2(kKeyEmpty, kKeyEmpty);
+                    else { a.key[p] = kKeyEmpty; a.key[p + 1] = kKeyEmpty; }
+                }
+                uint32_t out[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int i = 2 * r + j;
+                    out[j] = kHole;
+                    if (valid[i]) {
+                        const float phz = (pc[i].x - a.c.m0x) * a.c.mzx + (pc[i].y - a.c.m0y) * a.c.mzy + (pc[i].z - a.c.m0z) * a.c.mzz;
+                        out[j] = (uint32_t)(k[i] >> 32) + (col[i] & 255u);
+                        if (inr[i]) dback[(p + j) * 4 + 3] = phz;                 // the tile ray supplies colour and xyz, never w
+                        else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
+                    }
+                }
+                if (even && !inr[2 * r] && !inr[2 * r + 1]) *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
+                else { if (!inr[2 * r]) dscreen[p] = out[0]; if (!inr[2 * r + 1]) dscreen[p + 1] = out[1]; }
+            }
+            hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
         }
         const unsigned m = __ballot_sync(0xffffffffu, hole);
         if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(m);
-        __syncthreads();
-        // block counts / exclusive offsets inside the CTA
-        uint32_t blk_cnt[kGatherBlocksPerCta], cta_total = 0;
+        // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
+        // global atomic per CTA (a single counter hit by every pixel would serialise in L2)
+        unsigned int rflags = 0;
+        if (b < nblocks && !hole) {
 #pragma unroll
-        for (int i = 0; i < kGatherBlocksPerCta; ++i) { blk_cnt[i] = warp_cnt[2 * i] + warp_cnt[2 * i + 1]; cta_total += blk_cnt[i]; }
+            for (int i = 0; i < 4; ++i) {
+                const int px = x + (i & 1), py = y + (i >> 1);
+                if (!valid[i] && !inr[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
+            }
+        }
+        if (tid == 0) resid_cta_s = 0;
+        __syncthreads();
+        const unsigned int rcnt = (unsigned int)__popc(rflags);
+        unsigned int rofs = 0;
+        if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
+        __syncthreads();
+        if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
+        __syncthreads();
+        if (rflags) {
+            uint32_t *o = a.s.resid + resid_base_s + rofs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
+        }
+        uint32_t cta_total = 0, before_me = 0;
+#pragma unroll
+        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
+            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
+            if (i < (warp >> 1)) before_me += cnt;
+            cta_total += cnt;
+        }
+        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
         // decoupled look-back over the predecessors' aggregates (ticket order)
         if (warp == 0) {
-            const unsigned long long tag = (unsigned long long)epoch << 34;
+            const unsigned long long tag = (unsigned long long)a.epoch << 34;
             if (lane == 0) {
-                const unsigned long long v = tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total;
                 __threadfence();
-                atomicExch(&s.scan_state[ticket], v);
+                atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
             }
             uint32_t excl = 0;
             if (ticket > 0) {
                 int look = (int)ticket - 1;
                 while (true) {
-                    // each lane inspects one predecessor: look - lane
-                    const int idx = look - lane;
+                    const int idx = look - lane;                    // each lane inspects one predecessor
                     unsigned long long v = 0;
                     if (idx >= 0) {
-                        do { v = *reinterpret_cast<volatile unsigned long long *>(&s.scan_state[idx]); } while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0);
+                        do { v = *reinterpret_cast<volatile unsigned long long *>(&a.s.scan_state[idx]); }
+                        while ((v >> 34) != a.epoch || ((v >> 32) & 3ull) == 0);
                     }
                     const bool is_prefix = idx >= 0 && ((v >> 32) & 3ull) == 2ull;
                     const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                    // sum the values of lanes up to and including the first inclusive prefix
-                    const int first = pm ? __ffs(pm) - 1 : 31;
+                    const int first = pm ? __ffs(pm) - 1 : 31;      // sum up to and including the first inclusive prefix
                     uint32_t val = (idx >= 0 && lane <= first) ? (uint32_t)v : 0u;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
@@ -162,7 +257,7 @@ k_resolve_gather(uint32_t *__restrict__ screen, float *__restrict__ back, unsign
                 }
                 if (lane == 0) {
                     __threadfence();
-                    atomicExch(&s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
+                    atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
                 }
             }
             if (lane == 0) cta_prefix_s = excl;
@@ -170,109 +265,137 @@ k_resolve_gather(uint32_t *__restrict__ screen, float *__restrict__ back, unsign
         __syncthreads();
         const uint32_t cta_prefix = cta_prefix_s;
         if (b < nblocks) {
-            uint32_t ofs = cta_prefix;
-#pragma unroll
-            for (int i = 0; i < kGatherBlocksPerCta; ++i) if (i < (warp >> 1)) ofs += blk_cnt[i];
+            const uint32_t ofs = cta_prefix + before_me;
             if ((warp & 1) == 0 && lane == 0) {
-                if (b > 0) idb[b] = blk_cnt[warp >> 1];                     // raycast_counthole :273 (word 0 becomes the total)
-                idb[nblocks + b] = ofs;                                     // raycast_sumids :292
+                if (b > 0) a.idb[b] = my_block_cnt;                         // raycast_counthole :273 (word 0 becomes the total)
+                a.idb[nblocks + b] = ofs;                                   // raycast_sumids :292
             }
             if (hole) {
                 const uint32_t first_half = warp_cnt[warp & ~1];
                 const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
-                uint32_t *o = idb + 2 * (uint32_t)nblocks + ofs + ((warp & 1) ? first_half : 0u) + 4u * rank;
+                uint32_t *o = a.idb + 2 * (uint32_t)nblocks + ofs + ((warp & 1) ? first_half : 0u) + 4u * rank;
                 const uint32_t val = (uint32_t)x | ((uint32_t)y << 16);     // raycast_writeids :324,:334-337
                 o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
             }
         }
-        if (ticket == (unsigned)ncta - 1 && tid == 0) idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
+        if (ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
     }
     // the last CTA to finish re-arms the ticket counters for the next frame
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        const unsigned int done = atomicAdd(&s.counters[1], 1u);
-        if (done == gridDim.x - 1) { s.counters[0] = 0; s.counters[1] = 0; __threadfence(); }
+        const unsigned int done = atomicAdd(&a.s.counters[1], 1u);
+        if (done == gridDim.x - 1) { a.s.counters[0] = 0; a.s.counters[1] = 0; __threadfence(); }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// hole rays + tile-refresh rays as one list: work item w < idb[0] is a hole ray, the rest walk the gx*gy tile in
-// 8x4 footprints per warp.  64-thread CTAs so that a short list still lands on every SM.
-constexpr int kRaysBlock = 64;
+constexpr int kRaysBlock = 64;          // small CTAs: a short ray list still lands on every SM
 
+// raycast_holes: one ray per entry of the hole index buffer, count read from idb[0] on the device.
+// Short lists are latency bound (the kernel lasts as long as its slowest warp, a warp as long as the union of its lanes'
+// divergent paths), so with few rays each warp takes only 32/S of them and the idle SMs absorb the divergence.
 template <int D>
 __global__ void __launch_bounds__(kRaysBlock)
-k_rays(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
-       const uint32_t *__restrict__ idb, uint32_t root, int res_x, int res_y, int gx, int gy, int add_x, int add_y, RayCam cam)
+k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
+             const uint32_t *__restrict__ idb, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs)
 {
     __shared__ uint32_t stack[(D + 1) * kRaysBlock];
     const int idsize = (res_x / 16) * (res_y / 16);
-    const int nholes = (int)idb[0];
-    const int tiles_x = (gx + 7) / 8, tiles_y = (gy + 3) / 4;
-    const long long total = (long long)nholes + (long long)tiles_x * tiles_y * 32;
-    for (long long w = (long long)blockIdx.x * kRaysBlock + threadIdx.x; w < total; w += (long long)gridDim.x * kRaysBlock) {
-        int idx, idy;
-        if (w < nholes) {
-            const uint32_t idxy = idb[w + idsize * 2];
-            idx = (int)(idxy & 0xffffu); idy = (int)(idxy >> 16);
-        } else {
-            const int t = (int)(w - nholes);
-            const int fp = t >> 5, l = t & 31;
-            const int lx = (fp % tiles_x) * 8 + (l & 7), ly = (fp / tiles_x) * 4 + (l >> 3);
-            if (lx >= gx || ly >= gy) continue;
-            idx = lx + add_x; idy = ly + add_y;
-        }
+    const long long total = (long long)idb[0];
+    const long long nthreads = (long long)gridDim.x * kRaysBlock;
+    const int S = total * 4 <= nthreads ? 4 : total * 2 <= nthreads ? 2 : 1;
+    const long long gtid = (long long)blockIdx.x * kRaysBlock + threadIdx.x;
+    if (gtid % S) return;
+    for (long long w = gtid / S; w < total; w += nthreads / S) {
+        const uint32_t idxy = idb[w + idsize * 2];
+        const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+    }
+}
+
+// raycast_fine_2: the gx*gy rectangle at (add_x, add_y) in 8x4 footprints per warp
+template <int D>
+__global__ void __launch_bounds__(kRaysBlock)
+k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
+            int res_x, int res_y, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs)
+{
+    __shared__ uint32_t stack[(D + 1) * kRaysBlock];
+    const int tiles_x = (gx + 7) / 8, tiles_y = (gy + 3) / 4;
+    const int total = tiles_x * tiles_y * 32;
+    for (int t = blockIdx.x * kRaysBlock + threadIdx.x; t < total; t += gridDim.x * kRaysBlock) {
+        const int fp = t >> 5, l = t & 31;
+        const int lx = (fp % tiles_x) * 8 + (l & 7), ly = (fp / tiles_x) * 4 + (l >> 3);
+        if (lx >= gx || ly >= gy) continue;
+        const int idx = lx + add_x, idy = ly + add_y;
+        if (idx >= res_x || idy >= res_y) continue;
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cache copy + gap filter + colorize.  Each thread owns 4 consecutive pixels.
+// cache copy (optional) + colorize: 4 consecutive pixels per thread, no neighbours, no divergence.
 __global__ void __launch_bounds__(256)
-k_copy_fill_colorize(uint32_t *__restrict__ screen, float *__restrict__ back, uint32_t *__restrict__ tex,
-                     FusedScratch s, int res_x, int res_y, int target)
+k_copy_colorize(const uint32_t *__restrict__ src_s, const float4 *__restrict__ src_b, uint32_t *__restrict__ dst_s,
+                float4 *__restrict__ dst_b, uint32_t *__restrict__ tex, int n)
 {
-    const int n = res_x * res_y;
-    const bool vec = (n & 3) == 0;                      // 16-byte accesses need buffer strides that are multiples of 4 pixels
-    const int n4 = vec ? n >> 2 : 0, ntail = vec ? 0 : n;
-    uint32_t *dst_s = screen + (size_t)target * n;
-    float4 *dst_b = reinterpret_cast<float4 *>(back) + (size_t)target * n;
-    const float4 *src_b = reinterpret_cast<const float4 *>(back);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4 + ntail; q += gridDim.x * blockDim.x) {
-        const int p0 = q < n4 ? q * 4 : n4 * 4 + (q - n4), cnt = q < n4 ? 4 : 1;
-        uint32_t v[4] = {0u, 0u, 0u, 0u};
-        if (cnt == 4) { const uint4 t = *reinterpret_cast<const uint4 *>(screen + p0); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-        else v[0] = screen[p0];
-        float4 b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < cnt) b[i] = src_b[p0 + i];
-        if (cnt == 4) *reinterpret_cast<uint4 *>(dst_s + p0) = make_uint4(v[0], v[1], v[2], v[3]);
-        else dst_s[p0] = v[0];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < cnt) dst_b[p0 + i] = b[i];
-        if (tex == nullptr && !(v[0] == kHole || v[1] == kHole || v[2] == kHole || v[3] == kHole)) continue;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < cnt && v[i] == kHole) {
-            const int p = p0 + i, idx = p % res_x, idy = p / res_x;
-            if (idx >= res_x - 1 || idy >= res_y - 1 || idx <= 1 || idy <= 1) continue;      // kernel.cl:416
-            const uint32_t f = fillhole2_pixel(screen, p, res_x);                             // buffer 0 is not written by this kernel
-            if (f != kHole) { s.fixups[atomicAdd(&s.counters[2], 1u)] = make_uint2((uint32_t)p, f); v[i] = f; }
+    const bool vec = (n & 3) == 0 && (((uintptr_t)src_s | (uintptr_t)dst_s | (uintptr_t)tex) & 15u) == 0;
+    const int n4 = vec ? n >> 2 : 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+        const uint4 v = reinterpret_cast<const uint4 *>(src_s)[q];
+        if (dst_s) {
+            const float4 b0 = src_b[4 * q], b1 = src_b[4 * q + 1], b2 = src_b[4 * q + 2], b3 = src_b[4 * q + 3];
+            reinterpret_cast<uint4 *>(dst_s)[q] = v;
+            dst_b[4 * q] = b0; dst_b[4 * q + 1] = b1; dst_b[4 * q + 2] = b2; dst_b[4 * q + 3] = b3;
         }
-        if (tex) {
-            if (cnt == 4) *reinterpret_cast<uint4 *>(tex + p0) = make_uint4(colorize_word(v[0]), colorize_word(v[1]), colorize_word(v[2]), colorize_word(v[3]));
-            else tex[p0] = colorize_word(v[0]);
-        }
+        if (tex) reinterpret_cast<uint4 *>(tex)[q] = make_uint4(colorize_word(v.x), colorize_word(v.y), colorize_word(v.z), colorize_word(v.w));
+    }
+    for (int p = n4 * 4 + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t v = src_s[p];
+        if (dst_s) { dst_s[p] = v; dst_b[p] = src_b[p]; }
+        if (tex) tex[p] = colorize_word(v);
     }
 }
 
-__global__ void k_apply_fixups(uint32_t *__restrict__ screen, FusedScratch s)
+// gap filter on the listed pixels.  `snap` = the pre-filter image of pixels [0, n) (exact mode: the cache copy that
+// was just made; ping-pong: the destination slot itself, which this kernel does not write); reads at offsets >= n
+// (the 5x5 search near the last rows) come from `beyond`, the words that follow the image in the reference's layout.
+// out_s == nullptr: the filtered colour goes to the colorized image only.
+struct SnapView {
+    const uint32_t *snap, *beyond; int n;
+    __device__ __forceinline__ uint32_t operator[](int i) const { return i < n ? snap[i] : beyond[i]; }
+};
+__device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, int res_x)
 {
-    const unsigned int cnt = s.counters[2];             // reset by the next frame's k_proj_scatter2
+    const uint32_t c1 = s[ofs + 1], c2 = s[ofs - 1], c3 = s[ofs + res_x], c4 = s[ofs - res_x];
+    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
+        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
+    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
+    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+    uint32_t col = c1;                                   // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
+    if (col == kHole) col = c3;                          // i = 2
+    if (col == kHole) col = s[ofs + 1 + res_x];          // i = 3
+    if (col == kHole)
+        for (int i = -2; i < 3 && col == kHole; ++i)
+            for (int j = -2; j < 3; ++j) {
+                if (col != kHole) break;
+                col = s[ofs + i + j * res_x];
+            }
+    return col;
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_list(SnapView view, uint32_t *__restrict__ out_s, uint32_t *__restrict__ tex, const FusedScratch s, int res_x)
+{
+    const unsigned int cnt = s.resid_count[0];           // re-armed by the previous frame's k_proj_scatter2
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const uint2 f = s.fixups[i];
-        screen[f.x] = f.y;
+        const int p = (int)s.resid[i];
+        if (view[p] != kHole) continue;                  // listed before a ray filled it
+        const uint32_t f = fillhole2_view(view, p, res_x);
+        if (f == kHole) continue;                        // nothing within reach: stays a hole
+        if (out_s) out_s[p] = f;
+        if (tex) tex[p] = colorize_word(f);
     }
 }
 

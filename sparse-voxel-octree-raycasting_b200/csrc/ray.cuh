@@ -95,7 +95,8 @@ __device__ __forceinline__ uint32_t fetch_color(const uint32_t *__restrict__ oct
 template <int D, int STRIDE = kRayBlock>
 __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
-                                            int idx, int idy, const RayCam &c, uint32_t *stack)
+                                            int idx, int idy, const RayCam &c, uint32_t *stack,
+                                            unsigned int *resid_count = nullptr, uint32_t *resid = nullptr)
 {
     constexpr int kScaleMax = 1 << (D + 1);            // SCALE_MAX :19
     constexpr int kDepthAnd = (1 << D) - 1;            // OCTREE_DEPTH_AND :13
@@ -174,6 +175,9 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;
+    // a traced word can coincide with the hole marker (unmasked colour 0x00ffff00): the gap filter must see it
+    if (resid && 0xff000000u + col == kHole && idx > 1 && idy > 1 && idx < res_x - 1 && idy < res_y - 1)
+        resid[atomicAdd(resid_count, 1u)] = (uint32_t)ofs;
     float2 *b2 = reinterpret_cast<float2 *>(back + ofs * 4);
     *b2 = make_float2(px / 16.0f, py / 16.0f);
     back[ofs * 4 + 2] = pz / 16.0f;

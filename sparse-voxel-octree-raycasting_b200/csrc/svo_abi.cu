@@ -57,13 +57,19 @@ struct svo_mem_s {
 struct svo_ctx_s {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
+    cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
+    int last_slot = 0;                      // slot the last fused frame rendered into
+    bool have_frame = false;
     int num_sms = 148;
     int depth = 11;
     unsigned long long *key = nullptr;      // reprojection keys, one per destination pixel, kept armed (all ones)
     size_t key_pixels = 0;
     uint32_t *snap = nullptr;               // fillhole2 snapshot
     size_t snap_words = 0;
-    FusedScratch fs = {nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
+    const void *l2_pinned = nullptr;        // octree currently covered by the persisting-L2 access window
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    FusedScratch fs = {nullptr, nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
     size_t fs_ctas = 0, fs_pixels = 0;
     uint32_t epoch = 0;
     uint64_t launches = 0;
@@ -107,7 +113,14 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     cudaDeviceProp prop;
     CU_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
+    c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     return c;
 }
 
@@ -120,7 +133,10 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     if (c->snap) cudaFree(c->snap);
     if (c->fs.scan_state) cudaFree(c->fs.scan_state);
     if (c->fs.counters) cudaFree(c->fs.counters);
-    if (c->fs.fixups) cudaFree(c->fs.fixups);
+    if (c->fs.resid) cudaFree(c->fs.resid);
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamDestroy(c->stream2);
+    cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &e : c->prof_pool) cudaEventDestroy(e);
@@ -242,6 +258,7 @@ static void prof_flush(svo_ctx_t c)
 {
     if (c->prof_pending.empty()) return;
     CU_CHECK(cudaStreamSynchronize(c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream2));
     for (auto &r : c->prof_pending) {
         float ms = 0.f;
         CU_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
@@ -303,19 +320,20 @@ static cudaEvent_t prof_event(svo_ctx_t c)
 }
 // brackets one kernel launch: counts it, checks it, and (profiling only) times it with events on the stream
 struct LaunchScope {
-    svo_ctx_t c; const char *name; cudaEvent_t a = nullptr;
-    LaunchScope(svo_ctx_t ctx, const char *n) : c(ctx), name(n)
+    svo_ctx_t c; const char *name; cudaStream_t st; cudaEvent_t a = nullptr;
+    LaunchScope(svo_ctx_t ctx, const char *n, cudaStream_t stream = nullptr) : c(ctx), name(n), st(stream ? stream : ctx->stream)
     {
-        if (c->profiling) { a = prof_event(c); CU_CHECK(cudaEventRecord(a, c->stream)); }
+        if (c->profiling) { a = prof_event(c); CU_CHECK(cudaEventRecord(a, st)); }
     }
     ~LaunchScope()
     {
         c->launches++;
         CU_CHECK(cudaGetLastError());
-        if (a) { cudaEvent_t b = prof_event(c); CU_CHECK(cudaEventRecord(b, c->stream)); c->prof_pending.push_back({name, a, b}); }
+        if (a) { cudaEvent_t b = prof_event(c); CU_CHECK(cudaEventRecord(b, st)); c->prof_pending.push_back({name, a, b}); }
     }
 };
 #define LAUNCH(c, name) LaunchScope _ls((c), (name))
+#define LAUNCH_ON(c, name, stream) LaunchScope _ls((c), (name), (stream))
 
 static void ensure_key(svo_ctx_t c, size_t pixels)
 {
@@ -339,8 +357,8 @@ static void ensure_fused_scratch(svo_ctx_t c, size_t ctas, size_t pixels)
         c->fs_ctas = ctas;
     }
     if (c->fs_pixels < pixels) {
-        if (c->fs.fixups) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->fs.fixups)); }
-        CU_CHECK(cudaMalloc(&c->fs.fixups, pixels * 8));
+        if (c->fs.resid) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->fs.resid)); }
+        CU_CHECK(cudaMalloc(&c->fs.resid, pixels * 4));
         c->fs_pixels = pixels;
     }
 }
@@ -363,6 +381,24 @@ static void do_memcpy(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, const uint32_
 {
     if (!nwords) return;
     { LAUNCH(c, "k_memcpy"); k_memcpy<<<bw_grid(c, (nwords + 3) / 4), 256, 0, c->stream>>>(dst, dstofs, src, srcofs, nwords); }
+}
+
+// The node pool is the only data the ray kernels re-read across frames; the warping kernels stream ~100 MB per frame
+// through the same L2.  Keep the pool resident: persisting-L2 carve-out + an access-policy window on the stream.
+static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes)
+{
+    if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || getenv("SVO_NO_L2_PIN")) return;
+    const size_t win = bytes < c->l2_window_max ? bytes : c->l2_window_max;
+    const size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
+    CU_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    cudaStreamAttrValue attr = {};
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(oct);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU_CHECK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    c->l2_pinned = oct;
 }
 
 static ProjCam make_proj_cam(const float *m0, const float *mx, const float *my, const float *mz)
@@ -659,6 +695,7 @@ extern "C" void svo_end_all_kernels(void)                             // src/ocl
     svo_ctx_t c = need_ctx();
     if (!c) return;
     CU_CHECK(cudaStreamSynchronize(c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,44 +722,89 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     float *back = (float *)backbuffer->dptr;
     uint32_t *idb = (uint32_t *)idbuffer->dptr;
     const uint32_t *oct = (const uint32_t *)octree->dptr;
+    pin_octree_in_l2(c, oct, octree->bytes);
 
     const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     ensure_key(c, n);
     ensure_fused_scratch(c, ncta + 64, n);
     const bool strips = (res_x % 16) || (res_y % 16);
-
-    if (frame < 2) do_memset(c, screen, n, kHole, n * 3);                      // :150-154 (buffer 0 is rewritten below)
+    const bool pingpong = (p->flags & SVO_FRAME_PINGPONG) != 0;
+    // buffer roles (slots of the reference's 4-buffer arrays)
+    int dst_slot = 0, src_first = 1, src_count = 2;                       // exact: project buffers 1 and 2 into buffer 0
+    if (pingpong) {
+        dst_slot = (frame < 1 || !c->have_frame) ? 0 : (c->last_slot == 0 ? 2 : 0);
+        src_first = dst_slot == 0 ? 2 : 0; src_count = 1;
+    }
+    uint32_t *dscreen = screen + (size_t)dst_slot * n;
+    float *dback = back + (size_t)dst_slot * n * 4;
     const ProjCam pc = make_proj_cam(p->v0, p->rows[0], p->rows[1], p->rows[2]);
-    {   // :177-198 both source buffers, ascending source offset = the reference's launch order
-        LAUNCH(c, "k_proj_scatter2");
-        k_proj_scatter2<<<bw_grid(c, 2 * (size_t)n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, c->fs.counters + 2, res_x, res_y, pc);
-    }
-    {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
-        LAUNCH(c, "k_resolve_gather");
-        c->epoch = (c->epoch + 1) & 0x3fffffffu;
-        if (c->epoch == 0) c->epoch = 1;
-        k_resolve_gather<<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(screen, back, c->key, idb, c->fs, c->epoch, res_x, res_y, pc);
-    }
     const RayCam rc = make_ray_cam(p->v0, p->cols[0], p->cols[1], p->cols[2], p->fovx, p->fovy);
     const int add_x = (res_x / 8) * (frame & 7), add_y = (res_y / 4) * ((frame >> 3) & 3);   // :363-364
     const int gx = (int)svo_round_up(16, res_x / 8), gy = (int)svo_round_up(16, res_y / 4);
-    {   // :332-387 hole rays (count on the device) + tile refresh rays, one list
-        LAUNCH(c, "k_rays");
+    const Rect tile = {add_x, add_y, add_x + gx < res_x ? add_x + gx : res_x, add_y + gy < res_y ? add_y + gy : res_y};
+    const bool overlap = !getenv("SVO_NO_OVERLAP");
+    c->epoch = (c->epoch + 1) & 0x3fffffffu;
+    if (c->epoch == 0) c->epoch = 2;                                       // keeps the parity sequence alternating
+    c->fs.resid_count = c->fs.counters + 2 + (c->epoch & 1u);
+    unsigned int *next_resid_count = c->fs.counters + 2 + ((c->epoch + 1) & 1u);
+
+    if (frame < 2) {                                                       // :150-154 (the destination is rewritten below)
+        if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
+        else do_memset(c, screen, n, kHole, n * 3);
+    }
+    auto launch_tile = [&](cudaStream_t st) {                              // :361-387 tile refresh
+        LAUNCH_ON(c, "k_rays_tile", st);
+        const int grid = (((gx + 7) / 8) * ((gy + 3) / 4) * 32 + kRaysBlock - 1) / kRaysBlock;
+        if (c->depth == 11) k_rays_tile<11><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, c->fs);
+        else                k_rays_tile<14><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, c->fs);
+    };
+    if (overlap) {
+        // the tile rays depend on nothing of this frame: start them first, on the second stream, once the previous
+        // frame (which read and wrote the destination slot) has finished
+        CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
+        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
+        launch_tile(c->stream2);
+        CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
+    }
+    {   // :177-198 source buffers in ascending offset = the reference's launch order
+        LAUNCH(c, "k_proj_scatter2");
+        const unsigned int nsrc = (unsigned int)src_count * n;
+        k_proj_scatter2<<<bw_grid(c, nsrc, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, next_resid_count, res_x, res_y,
+                                                                        (unsigned int)src_first * n, nsrc, pc);
+    }
+    {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
+        LAUNCH(c, "k_resolve_gather");
+        GatherArgs ga = {screen, back, c->key, idb, c->fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc};
+        k_resolve_gather<<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
+    }
+    {   // :332-359 hole rays, count on the device
+        LAUNCH(c, "k_rays_holes");
         const int grid = c->num_sms * 32;
-        if (c->depth == 11) k_rays<11><<<grid, kRaysBlock, 0, c->stream>>>(screen, back, oct, idb, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc);
-        else                k_rays<14><<<grid, kRaysBlock, 0, c->stream>>>(screen, back, oct, idb, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc);
+        if (c->depth == 11) k_rays_holes<11><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, c->fs);
+        else                k_rays_holes<14><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, c->fs);
     }
-    {   // :394-437 cache copy (target 2) + gap filter + colorize
-        LAUNCH(c, "k_copy_fill_colorize");
-        k_copy_fill_colorize<<<bw_grid(c, (size_t)n / 4 + 4, 256, 8), 256, 0, c->stream>>>(
-            screen, back, screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr, c->fs, res_x, res_y, 2);
+    if (overlap) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
+    else launch_tile(c->stream);
+    uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
+    if (!pingpong || tex) {   // :394-405 cache copy (target 2) + :429-437 colorize
+        LAUNCH(c, "k_copy_colorize");
+        k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 4, 256, 8), 256, 0, c->stream>>>(
+            dscreen, reinterpret_cast<const float4 *>(dback), pingpong ? nullptr : screen + 2 * (size_t)n,
+            pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
     }
-    {
-        LAUNCH(c, "k_apply_fixups");
-        k_apply_fixups<<<32, 256, 0, c->stream>>>(screen, c->fs);
+    if (!pingpong || tex) {   // :411-422 gap filter on the listed hole pixels, reading the pre-filter image
+        LAUNCH(c, "k_fill_list");
+        // exact: snapshot = the copy in buffer 2, words past the image = what follows buffer 0 (buffer 1);
+        // ping-pong: the destination slot itself (never written here) and what follows it
+        SnapView view = {pingpong ? dscreen : screen + 2 * (size_t)n, dscreen, (int)n};
+        k_fill_list<<<c->num_sms * 2, 256, 0, c->stream>>>(view, pingpong ? nullptr : screen, tex, c->fs, res_x);
     }
+    c->last_slot = dst_slot;
+    c->have_frame = true;
     c->last_idbuf = idbuffer;
 }
+
+extern "C" int svo_frame_last_slot(void) { return g_ctx ? g_ctx->last_slot : 0; }
 
 extern "C" int svo_frame_idbuf_size(void)
 {

@@ -23,7 +23,10 @@ class FrameParams(C.Structure):
     """struct svo_frame_params (include/svo_b200.h)."""
     _fields_ = [("res_x", C.c_int), ("res_y", C.c_int), ("frame", C.c_int),
                 ("v0", C.c_float * 4), ("rows", (C.c_float * 4) * 3), ("cols", (C.c_float * 4) * 3),
-                ("fovx", C.c_float), ("fovy", C.c_float)]
+                ("fovx", C.c_float), ("fovy", C.c_float), ("flags", C.c_int)]
+
+
+FRAME_PINGPONG = 1
 
 
 def _sig(name, res, *args):
@@ -66,6 +69,7 @@ _svo_round_up = _sig("svo_round_up", _sz, _i, _i)
 _svo_launch_count = _sig("svo_launch_count", C.c_uint64)
 _svo_frame_fused = _sig("svo_frame_fused", None, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(FrameParams))
 _svo_frame_idbuf_size = _sig("svo_frame_idbuf_size", _i)
+_svo_frame_last_slot = _sig("svo_frame_last_slot", _i)
 
 _svo_event_record = _sig("svo_event_record", None, _i)
 _svo_event_elapsed_ms = _sig("svo_event_elapsed_ms", C.c_float, _i, _i)
@@ -237,6 +241,10 @@ def frame_fused(screen, back, idbuf, octree, root, tex, params):
     _svo_frame_fused(screen.handle, back.handle, idbuf.handle, octree.handle, root, tex.handle if tex else None,
                      C.byref(params))
     _check()
+
+
+def frame_last_slot():
+    return int(_svo_frame_last_slot())
 
 
 def frame_idbuf_size():

@@ -8,6 +8,9 @@ WASD -> pos, :113-133) is set explicitly with ``set_camera(pos, rot)``; the GL b
 ``mode="reference"`` issues the reference's 13 launches one by one through ocl_begin/ocl_param/ocl_end with the
 argument lists of the call sites, including the blocking 4-byte readback of idbuf_size (:298).
 ``mode="fused"`` issues the same frame through ``svo_frame_fused`` (no host readback); results are identical.
+``mode="pingpong"`` is the fused frame with SVO_FRAME_PINGPONG: no cache copy, frames alternate between buffers 0 and 2
+(``last_slot()`` says where the frame is); the id buffer and the colorized image are identical to the reference's, the
+slot rendered into holds what the reference's cache buffer 2 holds.
 """
 import ctypes as C
 import math
@@ -126,7 +129,7 @@ def raycast_draw(res_x, res_y):
     rows = [m[i, :].copy() for i in range(3)]                                      # :160-162
     cols = [m[:, i].copy() for i in range(3)]                                      # :322-325
     S.last_camera = dict(pos=pos.copy(), v0=v0, rows=rows, cols=cols)
-    if S.mode == "fused":
+    if S.mode in ("fused", "pingpong"):
         p = ocl.FrameParams()
         p.res_x, p.res_y, p.frame = res_x, res_y, frame
         p.v0[:] = v0.tolist()
@@ -134,6 +137,7 @@ def raycast_draw(res_x, res_y):
             p.rows[i][:] = rows[i].tolist()
             p.cols[i][:] = cols[i].tolist()
         p.fovx, p.fovy = fovx, fovy
+        p.flags = ocl.FRAME_PINGPONG if S.mode == "pingpong" else 0
         ocl.ocl_begin_all_kernels()
         ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal,
                         S.mem_screenbuffer_tex, p)
@@ -223,6 +227,7 @@ def prepare_params(res_x, res_y, frame):
         p.rows[i][:] = m[i, :].tolist()
         p.cols[i][:] = m[:, i].tolist()
     p.fovx = p.fovy = 1.0
+    p.flags = ocl.FRAME_PINGPONG if S.mode == "pingpong" else 0
     return p
 
 
@@ -267,7 +272,12 @@ def full_raycast_ms(res_x, res_y, repeats=5):
 
 
 def idbuf_size():
-    return ocl.frame_idbuf_size() if S.mode == "fused" else S.idbuf_size
+    return ocl.frame_idbuf_size() if S.mode in ("fused", "pingpong") else S.idbuf_size
+
+
+def last_slot():
+    """Buffer index the last frame was rendered into (0, or 0/2 alternating in ping-pong mode)."""
+    return ocl.frame_last_slot() if S.mode == "pingpong" else 0
 
 
 def read_frame(res_x, res_y):

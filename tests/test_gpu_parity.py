@@ -213,6 +213,46 @@ def test_frame_sequence(svo, orc, world, mode, res, nframes):
         svo.ocl_init(0)
 
 
+@pytest.mark.parametrize("res,nframes", [((320, 192), 36), ((200, 120), 6), ((1920, 1024), 4)])
+def test_frame_sequence_pingpong(svo, orc, world, res, nframes):
+    """SVO_FRAME_PINGPONG: no cache copy.  The id buffer and the colorized image are the reference's; the slot rendered
+    into holds what the reference's cache buffer 2 holds (colour words and xyzw)."""
+    octree, root = world
+    rx, ry = res
+    n = rx * ry
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4)
+    rc = svo.raycast
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="pingpong")
+    try:
+        for f in range(nframes):
+            pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
+            O.draw(pos, rot)
+            rc.set_camera(pos, rot)
+            rc.raycast_draw(rx, ry)
+            slot = rc.last_slot()
+            assert slot == (0 if f % 2 == 0 else 2)
+            screen, back, idb = rc.read_buffers(rx, ry)
+            assert rc.idbuf_size() == O.idbuf_size, f"frame {f}"
+            assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"frame {f} ids"
+            assert np.array_equal(screen[slot * n:(slot + 1) * n], O.screen[2 * n:3 * n]), f"frame {f} colour"
+            got = back[slot * 4 * n:(slot + 1) * 4 * n].view(np.uint32).reshape(n, 4)
+            exp = O.back[8 * n:12 * n].view(np.uint32).reshape(n, 4)
+            # xyz of a pixel that is still a hole is whatever an older frame left there (never read: the reprojection
+            # skips holes, kernel.cl:499); compare the positions of all non-hole pixels
+            live = O.screen[2 * n:3 * n] != HOLE
+            assert np.array_equal(got[live, :3], exp[live, :3]), f"frame {f} xyz"
+            # w (camera z) is written by the reprojection only; for ray-filled pixels the reference keeps whatever an
+            # older frame left in buffer 0 (dead data no enabled kernel reads) and the alternating slots keep another
+            # stale value.  Compare w where this frame's reprojection wrote it.
+            proj = live & ((O.screen[2 * n:3 * n] >> 24) != 0xff)
+            assert np.array_equal(got[proj, 3], exp[proj, 3]), f"frame {f} w"
+            assert np.array_equal(rc.read_frame(rx, ry).ravel(), O.tex), f"frame {f} tex"
+    finally:
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
 def test_golden_frames(svo):
     """The CUDA path against the committed vectors produced by the reference's own source (tests/golden)."""
     from golden.make_golden import golden_pose, NFRAMES
