@@ -245,7 +245,13 @@ def test_frame_sequence_pingpong(svo, orc, world, res, nframes):
             # w (camera z) is written by the reprojection only; for ray-filled pixels the reference keeps whatever an
             # older frame left in buffer 0 (dead data no enabled kernel reads) and the alternating slots keep another
             # stale value.  Compare w where this frame's reprojection wrote it.
-            proj = live & ((O.screen[2 * n:3 * n] >> 24) != 0xff)
+            traced = np.zeros(n, dtype=bool)
+            ids = O.idbuf[2 * O.nblocks:2 * O.nblocks + O.idbuf_size]
+            traced[(ids & 0xffff).astype(np.int64) + (ids >> 16).astype(np.int64) * rx] = True
+            ax, ay = O.tile()
+            tmask = np.zeros((ry, rx), dtype=bool)
+            tmask[ay:ay + -(-(ry // 4) // 16) * 16, ax:ax + -(-(rx // 8) // 16) * 16] = True
+            proj = live & ~traced & ~tmask.ravel()
             assert np.array_equal(got[proj, 3], exp[proj, 3]), f"frame {f} w"
             assert np.array_equal(rc.read_frame(rx, ry).ravel(), O.tex), f"frame {f} tex"
     finally:

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Condense an ncu report (.ncu-rep) into the per-kernel table kept under profiles/.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.md"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = [("gpu__time_duration.sum", "time_us"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("launch__registers_per_thread", "regs"),
+        ("smsp__inst_executed.sum", "warp_inst"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_act%"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_act%"),
+        ("l1tex__t_sector_hit_rate.pct", "l1_hit%"), ("lts__t_sector_hit_rate.pct", "l2_hit%"),
+        ("lts__t_bytes.sum", "l2_bytes"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall_branch"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_sel"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg")]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    cols = [(hdr.index(m), s) for m, s in WANT if m in hdr]
+    print(f"# ncu --set full summary of `{rep}` (one row per profiled launch; cold-cache replays, compare shares not absolutes)\n")
+    print("| kernel | " + " | ".join(f"{s} [{units[i]}]" if units[i] else s for i, s in cols) + " |")
+    print("|---|" + "---|" * len(cols))
+    for r in rows[2:]:
+        vals = []
+        for i, _ in cols:
+            v = r[i].replace(",", "")
+            try:
+                v = f"{float(v):.4g}"
+            except ValueError:
+                pass
+            vals.append(v)
+        print("| " + r[ki].split("(")[0].replace("void ", "") + " | " + " | ".join(vals) + " |")
+
+
+if __name__ == "__main__":
+    main()
