@@ -20,9 +20,12 @@ def lib():
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "svo_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(svo_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for h in ("svo_b200.h", "svo_host.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(svo_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_declares_the_ocl_surface():
