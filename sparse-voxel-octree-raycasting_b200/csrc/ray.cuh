@@ -128,20 +128,26 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     float distance = 0.f, lodswitch = (float)(res_x * 2);          // res_x*LOD_ADJUST*2 :663
     int guard = 1 << 20;                                           // never reached; bounds a corrupt octree
 
-    do {
-        const int cx = ix >> rekursion, cy = iy >> rekursion, cz = iz >> rekursion;
-        const int node_index = ((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) ^ sign_xyz;
-        node_test = nodeid & (1u << node_index);
-        if (node_test) {
+    // The reference's loop takes one of two branches per iteration (descend into an occupied child / step through an
+    // empty cell).  Same per-ray sequence, arranged "while-while": the lanes of a warp first run their descents together,
+    // then all step together, instead of paying for both branches on every trip once they fall out of phase.
+    for (;;) {
+        int cx, cy, cz;
+        bool hit = false;
+        for (;;) {                                                     // descend while the child under the ray is occupied
+            cx = ix >> rekursion; cy = iy >> rekursion; cz = iz >> rekursion;
+            const int node_index = ((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) ^ sign_xyz;
+            node_test = nodeid & (1u << node_index);
+            if (!node_test) break;
             const uint32_t tmp = nodeid;
             nodeid = fetch_child(oct, nodeid, before, local_root, (uint32_t)node_index, node_test, rekursion);
             before = tmp;
-            if (rekursion <= lod) break;
+            if (rekursion <= lod) { hit = true; break; }               // :172
             --rekursion;
             stack[rekursion * STRIDE] = nodeid;
-            continue;
         }
-        const float mx = (float)((cx + 1) << rekursion) - px;
+        if (hit) break;
+        const float mx = (float)((cx + 1) << rekursion) - px;          // :181 step to the nearest face of the current cell
         const float my = (float)((cy + 1) << rekursion) - py;
         const float mz = (float)((cz + 1) << rekursion) - pz;
         float dist = mx * len0;
@@ -155,17 +161,19 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
         x0ry = iy ^ ny;
         const int x0r = ((ix ^ nx) ^ x0ry ^ (iz ^ nz)) & kDepthAnd;
         ix = nx; iy = ny; iz = nz;
-        if (distance > kViewDistMax) break;
-        // (int)log2((float)x0r): floor(log2) for x0r>0, INT_MIN for 0  ->  "x0r < 2^rekursion" means stay
-        if ((x0r >> rekursion) == 0) continue;
-        rekursion = 32 - __clz(x0r);                               // rekursion_new + 1
-        if (rekursion >= D) { nodeid = before = root; }
-        else {
-            nodeid = stack[rekursion * STRIDE];
-            before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
+        if (distance > kViewDistMax) break;                            // :203
+        // (int)log2((float)x0r): floor(log2) for x0r>0, INT_MIN for 0  ->  "x0r < 2^rekursion" means stay in this node
+        if ((x0r >> rekursion) != 0) {
+            rekursion = 32 - __clz(x0r);                               // rekursion_new + 1
+            if (rekursion >= D) { nodeid = before = root; }
+            else {
+                nodeid = stack[rekursion * STRIDE];
+                before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
+            }
+            if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }    // :209
         }
-        if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }
-    } while (!(x0ry & (2 * kDepthAnd + 2)) && --guard);
+        if ((x0ry & (2 * kDepthAnd + 2)) || !--guard) break;           // :211 the ray left the world through y
+    }
 
     if (sign_xyz & 1) px = (float)kScaleMax - px;
     if (sign_xyz & 2) py = (float)kScaleMax - py;
