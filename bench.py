@@ -66,6 +66,21 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
+        try:                                   # NVML in-process: a sample every ~5 ms (the timed region is ~50 ms)
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            while not self.stop_flag:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)]
+                                    + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.005)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -239,14 +254,18 @@ def main():
     rc.reset_frames()
     for f in range(args.warmup):
         rc.draw_prepared(P[f], sync=True)
-    host_frame = ocl.host_alloc(n * 4)
+    host_frames = [ocl.host_alloc(n * 4), ocl.host_alloc(n * 4)]
     sync_all()
     t0 = time.perf_counter()
     for f in range(args.warmup, total):
-        rc.draw_prepared(P[f], sync=False)                        # host -> device: the frame's camera block (kernel arguments)
-        ocl.copy_to_host_async(host_frame, rc.S.mem_screenbuffer_tex, n * 4)
-        ocl.ocl_end_all_kernels()                                  # the caller owns the finished frame here
+        # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame, read back
+        # on the copy stream while the next frame renders.  The caller owns frame f-1 after present_wait.
+        k = rc.draw_present(P[f], host_frames)
+        if f > args.warmup:
+            ocl.present_wait(k ^ 1)
+    ocl.present_wait(k)
     e2e_s = time.perf_counter() - t0
+    host_frame = host_frames[k]
     sampler.stop_flag = True
     sampler.join()
     checksum = int(np.frombuffer(host_frame, dtype=np.uint32, count=n).sum(dtype=np.uint64))

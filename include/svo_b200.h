@@ -86,6 +86,12 @@ void  *svo_host_alloc(size_t bytes);
 void   svo_host_free(void *p);
 void   svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, size_t srcofs);   /* ordered on the stream; svo_end_all_kernels() waits */
 
+/* headless present (replaces the PBO -> texture blit, src/raycast.h:449-455): copy `size` bytes of the colorized frame to
+ * page-locked host memory on a copy stream once the launches issued so far have finished; the next frame may be issued
+ * immediately (give it another colorize target).  slot 0..3; svo_present_wait(slot) blocks until that copy has landed. */
+void   svo_present_async(void *host_dst, svo_mem_t src, size_t size, int slot);
+void   svo_present_wait(int slot);
+
 /* ---- fused frame (B200-native fast path; same results as the 13-launch sequence of
  *      raycast_draw, src/raycast.h:147-438, without the mid-frame host readback) ------------------ */
 typedef struct svo_frame_params {

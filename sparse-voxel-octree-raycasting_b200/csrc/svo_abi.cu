@@ -75,6 +75,8 @@ struct svo_ctx_s {
     uint64_t launches = 0;
     svo_mem_t last_idbuf = nullptr;         // id buffer of the last fused frame (word 0 = idbuf_size)
     cudaEvent_t events[16] = {};
+    cudaStream_t copy_stream = nullptr;     // svo_present_async: frame read-back overlapped with the next frame
+    cudaEvent_t present_ready[4] = {}, present_done[4] = {};
     // per-kernel profiling (svo_profile_*)
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -138,6 +140,9 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamDestroy(c->stream2);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (auto &e : c->present_ready) if (e) cudaEventDestroy(e);
+    for (auto &e : c->present_done) if (e) cudaEventDestroy(e);
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -235,6 +240,33 @@ extern "C" void svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, si
     if (!c) return;
     if (!src || srcofs + size > src->bytes) { svo_fail(-104, "svo_copy_to_host_async out of range"); return; }
     CU_CHECK(cudaMemcpyAsync(dst, (const char *)src->dptr + srcofs, size, cudaMemcpyDeviceToHost, c->stream));
+}
+
+// Headless "present": the finished frame goes to (pinned) host memory on a separate copy stream, so the next frame's
+// kernels overlap the PCIe transfer.  The reference's equivalent is the PBO -> texture blit after raycast_draw
+// (src/raycast.h:449-455), which is device-side and equally asynchronous to the next frame's enqueues.
+extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, int slot)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!src || size > src->bytes || slot < 0 || slot >= 4) { svo_fail(-108, "svo_present_async: bad arguments"); return; }
+    if (!c->copy_stream) {
+        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) {
+            CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
+            CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
+        }
+    }
+    CU_CHECK(cudaEventRecord(c->present_ready[slot], c->stream));
+    CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->present_ready[slot], 0));
+    CU_CHECK(cudaMemcpyAsync(host_dst, src->dptr, size, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU_CHECK(cudaEventRecord(c->present_done[slot], c->copy_stream));
+}
+extern "C" void svo_present_wait(int slot)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || slot < 0 || slot >= 4 || !c->present_done[slot]) return;
+    CU_CHECK(cudaEventSynchronize(c->present_done[slot]));
 }
 
 // ---- timing -----------------------------------------------------------------------------------------

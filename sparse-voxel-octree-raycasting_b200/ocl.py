@@ -81,6 +81,9 @@ _svo_host_alloc = _sig("svo_host_alloc", _vp, _sz)
 _svo_host_free = _sig("svo_host_free", None, _vp)
 _svo_copy_to_host_async = _sig("svo_copy_to_host_async", None, _vp, _vp, _sz, _sz)
 
+_svo_present_async = _sig("svo_present_async", None, _vp, _vp, _sz, _i)
+_svo_present_wait = _sig("svo_present_wait", None, _i)
+
 _raise_errors = False
 
 
@@ -291,4 +294,15 @@ def host_alloc(nbytes):
 
 def copy_to_host_async(dst, src, size, srcofs=0):
     _svo_copy_to_host_async(C.addressof(dst), src.handle, size, srcofs)
+    _check()
+
+
+def present_async(dst, src, size, slot):
+    """Frame read-back on the copy stream (overlaps the next frame); present_wait(slot) blocks until it has landed."""
+    _svo_present_async(C.addressof(dst), src.handle, size, slot)
+    _check()
+
+
+def present_wait(slot):
+    _svo_present_wait(slot)
     _check()

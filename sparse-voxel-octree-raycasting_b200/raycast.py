@@ -86,6 +86,7 @@ def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth
     S.mem_backbuffer = ocl.ocl_malloc(size * 16 * 4)                               # :82
     S.mem_screenbuffer = ocl.ocl_malloc(size * 4 * 4)                              # :85
     S.mem_screenbuffer_tex = ocl.ocl_malloc(size * 4)                              # PBO stand-in (:88-89)
+    S.mem_screenbuffer_tex2 = None                                                 # second colorize target (draw_present)
     S.mem_x = S.mem_y = None                                                       # dead kernel arguments (:170-171)
     S.mem_z = ocl.ocl_malloc(4 * size)                                             # :172 (only ever memset)
     # :268-270 allocates MAXPIX + MAXB words, but counts + offsets + ids need N + 2B: the reference overruns by B words
@@ -240,6 +241,20 @@ def draw_prepared(p, sync=True):
         ocl.ocl_end_all_kernels()
 
 
+def draw_present(p, host_frames):
+    """Pipelined headless frame: frame p.frame is rendered into colorize target (p.frame & 1) and its read-back into
+    host_frames[p.frame & 1] (page-locked, ocl.host_alloc) is queued on the copy stream, so it overlaps the next frame.
+    The caller owns the image after ocl.present_wait(p.frame & 1)."""
+    if S.mem_screenbuffer_tex2 is None:
+        S.mem_screenbuffer_tex2 = ocl.ocl_malloc(S.mem_screenbuffer_tex.size)
+    k = p.frame & 1
+    tex = S.mem_screenbuffer_tex2 if k else S.mem_screenbuffer_tex
+    S.frame = p.frame
+    ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
+    ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 4, k)
+    return k
+
+
 def reset_frames():
     S.frame = -1
 
@@ -299,7 +314,7 @@ def raycast_exit():
     """src/raycast.h:511-517."""
     if not S.ready:
         return
-    for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_z", "mem_idbuffer"):
+    for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_screenbuffer_tex2", "mem_z", "mem_idbuffer"):
         m = getattr(S, name, None)
         if m is not None:
             m.free()
