@@ -119,6 +119,41 @@ int  svo_frame_idbuf_size(void);
 /* buffer index (0 or 2) the last fused frame was rendered into; always 0 without SVO_FRAME_PINGPONG */
 int  svo_frame_last_slot(void);
 
+/* ---- screen bands across the GPUs of one box (extension: the reference is single-device, src/ocl.h:89,127,140) ----
+ * The screen is cut into stripes of `stripe_rows` rows (rounded up to a multiple of the 16-row hole block; <= 0 selects
+ * nranks contiguous bands); stripe s belongs to rank s % nranks.  Every rank holds the octree and full-size buffers laid
+ * out like the reference's (src/raycast.h:79-85) but owns only its rows.  The frame is the fused frame above with the
+ * reprojection's depth test resolved by 64-bit atomicMin straight into the owner's key buffer over NVLink, peer gathers of
+ * the winners, colorized rows stored into rank 0's frame, and flag barriers in peer memory; results are bit-identical to
+ * one GPU.  One band per context; create the context first (svo_init / svo_ctx_create + svo_ctx_set_current) and
+ * svo_malloc the octree in it. */
+typedef struct svo_band_s *svo_band_t;
+enum { SVO_IPC_HANDLE_BYTES = 64, SVO_BAND_MAX_RANKS = 8 };
+typedef struct svo_band_handles { unsigned char mem[6][SVO_IPC_HANDLE_BYTES]; } svo_band_handles;  /* screen back key halo tex flags */
+enum { SVO_BAND_SCREEN = 0, SVO_BAND_BACK = 1, SVO_BAND_IDBUF = 2, SVO_BAND_TEX = 3, SVO_BAND_HALO = 4 };
+
+/* pure host arithmetic (no device needed): out = {effective stripe rows, rows owned, whole 16-row block rows owned, stripes owned} */
+int  svo_band_layout(int rank, int nranks, int res_x, int res_y, int stripe_rows, int out[4]);
+int  svo_band_owner(int y, int nranks, int effective_stripe_rows);
+
+svo_band_t svo_band_create(int rank, int nranks, int res_x, int res_y, int stripe_rows, svo_mem_t octree, uint32_t octree_root);
+void svo_band_destroy(svo_band_t band);
+/* one process per GPU: exchange the handles (any transport), then connect; all[nranks], own entry ignored */
+void svo_band_get_handles(svo_band_t band, svo_band_handles *out);
+void svo_band_connect_ipc(svo_band_t band, const svo_band_handles *all);
+/* one process driving several devices (or several bands on one device, for tests): all[nranks] */
+void svo_band_connect_local(svo_band_t band, const svo_band_t *all);
+/* this rank's part of one frame / of one full raycast (asynchronous); every rank must issue the same call sequence */
+void svo_band_frame(svo_band_t band, const svo_frame_params *p);
+void svo_band_raycast(svo_band_t band, const svo_frame_params *p);
+void svo_band_sync(svo_band_t band);                       /* waits for this rank; reports a peer that never reached a barrier */
+/* blocking access to this rank's buffers (SVO_BAND_*); id buffer layout: [0,Bl) counts ([0] = total), [Bl,2Bl) offsets, ids */
+int  svo_band_read(svo_band_t band, int which, void *dst, size_t bytes, size_t offset);
+int  svo_band_write(svo_band_t band, int which, const void *src, size_t bytes, size_t offset);
+svo_ctx_t svo_band_ctx(svo_band_t band);
+int  svo_band_last_slot(svo_band_t band);
+void *svo_band_tex_device_ptr(svo_band_t band);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,9 +11,9 @@ and a missing GPU raises at ``ocl_init()``.
 from .ocl import (Device, Mem, ocl_init, ocl_exit, ocl_get_kernel, ocl_malloc, ocl_copy_to_host, ocl_copy_to_device,
                   ocl_begin, ocl_param, ocl_end, ocl_begin_all_kernels, ocl_end_all_kernels, ocl_memcpy, ocl_memset,
                   ocl_round_up, lib, LIB_PATH, FrameParams, launch_count, set_octree_depth)
-from . import raycast, scene  # noqa: F401
+from . import raycast, scene, bands  # noqa: F401
 
 __all__ = ["Device", "Mem", "ocl_init", "ocl_exit", "ocl_get_kernel", "ocl_malloc", "ocl_copy_to_host",
            "ocl_copy_to_device", "ocl_begin", "ocl_param", "ocl_end", "ocl_begin_all_kernels", "ocl_end_all_kernels",
            "ocl_memcpy", "ocl_memset", "ocl_round_up", "lib", "LIB_PATH", "FrameParams", "launch_count",
-           "set_octree_depth", "raycast", "scene"]
+           "set_octree_depth", "raycast", "scene", "bands"]

@@ -1,0 +1,80 @@
+// abi_internal.h -- shared between the translation units of libsvo_b200.so (svo_abi.cu, svo_bands.cu): context and
+// buffer structs behind the opaque handles of include/svo_b200.h, error helper, launch bracket.
+#pragma once
+#include "../../include/svo_b200.h"
+#include "fused.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+void svo_fail(int code, const char *fmt, ...);
+
+#define CU_CHECK(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) svo_fail((int)_e, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+    } while (0)
+
+struct svo_mem_s {
+    void *dptr;
+    size_t bytes;
+    int device;
+};
+
+using svo::FusedScratch;
+
+struct svo_ctx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
+    cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
+    int last_slot = 0;                      // slot the last fused frame rendered into
+    bool have_frame = false;
+    int num_sms = 148;
+    int depth = 11;
+    unsigned long long *key = nullptr;      // reprojection keys, one per destination pixel, kept armed (all ones)
+    size_t key_pixels = 0;
+    uint32_t *snap = nullptr;               // fillhole2 snapshot
+    size_t snap_words = 0;
+    const void *l2_pinned = nullptr;        // octree currently covered by the persisting-L2 access window
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    FusedScratch fs = {nullptr, nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
+    size_t fs_ctas = 0, fs_pixels = 0;
+    uint32_t epoch = 0;
+    uint64_t launches = 0;
+    svo_mem_t last_idbuf = nullptr;         // id buffer of the last fused frame (word 0 = idbuf_size)
+    cudaEvent_t events[16] = {};
+    cudaStream_t copy_stream = nullptr;     // svo_present_async: frame read-back overlapped with the next frame
+    cudaEvent_t present_ready[4] = {}, present_done[4] = {};
+    // per-kernel profiling (svo_profile_*)
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    std::map<std::string, std::pair<double, uint64_t>> prof_acc;
+};
+
+svo_ctx_t svo_need_ctx();
+cudaEvent_t svo_prof_event(svo_ctx_t c);
+void svo_pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes);
+
+// brackets one kernel launch: counts it, checks it, and (profiling only) times it with events on the stream
+struct LaunchScope {
+    svo_ctx_t c; const char *name; cudaStream_t st; cudaEvent_t a = nullptr;
+    LaunchScope(svo_ctx_t ctx, const char *n, cudaStream_t stream = nullptr) : c(ctx), name(n), st(stream ? stream : ctx->stream)
+    {
+        if (c->profiling) { a = svo_prof_event(c); CU_CHECK(cudaEventRecord(a, st)); }
+    }
+    ~LaunchScope()
+    {
+        c->launches++;
+        CU_CHECK(cudaGetLastError());
+        if (a) { cudaEvent_t b = svo_prof_event(c); CU_CHECK(cudaEventRecord(b, st)); c->prof_pending.push_back({name, a, b}); }
+    }
+};
+#define LAUNCH(c, name) LaunchScope _ls((c), (name))
+#define LAUNCH_ON(c, name, stream) LaunchScope _ls((c), (name), (stream))

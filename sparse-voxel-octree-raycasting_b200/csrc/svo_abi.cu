@@ -1,18 +1,9 @@
 // svo_abi.cu -- the C ABI of libsvo_b200.so (include/svo_b200.h): context, device memory, and the
 // ocl_begin / ocl_param / ocl_end style launch marshalling of the reference's src/ocl.h, dispatching to the
 // hand-written sm_100a kernels in ray.cuh / warp.cuh.  No OpenCL, no run-time source build, no CPU fallback.
-#include "../../include/svo_b200.h"
-#include "ray.cuh"
-#include "warp.cuh"
-#include "fused.cuh"
+#include "abi_internal.h"
 
 #include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
 
 using namespace svo;
 
@@ -23,7 +14,7 @@ static int g_error_mode = SVO_ERRORS_ABORT;
 static int g_last_error = 0;
 static char g_last_error_str[512] = "";
 
-static void svo_fail(int code, const char *fmt, ...)
+void svo_fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -34,56 +25,10 @@ static void svo_fail(int code, const char *fmt, ...)
     if (g_error_mode == SVO_ERRORS_ABORT) abort();
 }
 
-#define CU_CHECK(expr)                                                                             \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess) svo_fail((int)_e, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
-    } while (0)
-
 extern "C" void svo_set_error_mode(int mode) { g_error_mode = mode; }
 extern "C" int svo_last_error(void) { return g_last_error; }
 extern "C" const char *svo_last_error_string(void) { return g_last_error_str; }
 extern "C" void svo_clear_error(void) { g_last_error = 0; g_last_error_str[0] = 0; }
-
-// ------------------------------------------------------------------------------------------------
-// context / memory
-// ------------------------------------------------------------------------------------------------
-struct svo_mem_s {
-    void *dptr;
-    size_t bytes;
-    int device;
-};
-
-struct svo_ctx_s {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
-    cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
-    int last_slot = 0;                      // slot the last fused frame rendered into
-    bool have_frame = false;
-    int num_sms = 148;
-    int depth = 11;
-    unsigned long long *key = nullptr;      // reprojection keys, one per destination pixel, kept armed (all ones)
-    size_t key_pixels = 0;
-    uint32_t *snap = nullptr;               // fillhole2 snapshot
-    size_t snap_words = 0;
-    const void *l2_pinned = nullptr;        // octree currently covered by the persisting-L2 access window
-    size_t l2_persist_max = 0, l2_window_max = 0;
-    FusedScratch fs = {nullptr, nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
-    size_t fs_ctas = 0, fs_pixels = 0;
-    uint32_t epoch = 0;
-    uint64_t launches = 0;
-    svo_mem_t last_idbuf = nullptr;         // id buffer of the last fused frame (word 0 = idbuf_size)
-    cudaEvent_t events[16] = {};
-    cudaStream_t copy_stream = nullptr;     // svo_present_async: frame read-back overlapped with the next frame
-    cudaEvent_t present_ready[4] = {}, present_done[4] = {};
-    // per-kernel profiling (svo_profile_*)
-    bool profiling = false;
-    struct ProfRec { const char *name; cudaEvent_t a, b; };
-    std::vector<ProfRec> prof_pending;
-    std::vector<cudaEvent_t> prof_pool;
-    std::map<std::string, std::pair<double, uint64_t>> prof_acc;
-};
 
 static svo_ctx_t g_ctx = nullptr;           // current context (the reference's globals, src/ocl.h:8-16)
 
@@ -92,6 +37,7 @@ static svo_ctx_t need_ctx()
     if (!g_ctx) svo_fail(-100, "no context: call svo_init() first");
     return g_ctx;
 }
+svo_ctx_t svo_need_ctx() { return need_ctx(); }
 
 extern "C" int svo_device_count(void)
 {
@@ -343,29 +289,13 @@ static inline int bw_grid(svo_ctx_t c, size_t items, int block = 256, int per_sm
     return g ? (int)g : 1;
 }
 
-static cudaEvent_t prof_event(svo_ctx_t c)
+cudaEvent_t svo_prof_event(svo_ctx_t c)
 {
     cudaEvent_t e;
     if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     CU_CHECK(cudaEventCreate(&e));
     return e;
 }
-// brackets one kernel launch: counts it, checks it, and (profiling only) times it with events on the stream
-struct LaunchScope {
-    svo_ctx_t c; const char *name; cudaStream_t st; cudaEvent_t a = nullptr;
-    LaunchScope(svo_ctx_t ctx, const char *n, cudaStream_t stream = nullptr) : c(ctx), name(n), st(stream ? stream : ctx->stream)
-    {
-        if (c->profiling) { a = prof_event(c); CU_CHECK(cudaEventRecord(a, st)); }
-    }
-    ~LaunchScope()
-    {
-        c->launches++;
-        CU_CHECK(cudaGetLastError());
-        if (a) { cudaEvent_t b = prof_event(c); CU_CHECK(cudaEventRecord(b, st)); c->prof_pending.push_back({name, a, b}); }
-    }
-};
-#define LAUNCH(c, name) LaunchScope _ls((c), (name))
-#define LAUNCH_ON(c, name, stream) LaunchScope _ls((c), (name), (stream))
 
 static void ensure_key(svo_ctx_t c, size_t pixels)
 {
@@ -417,6 +347,8 @@ static void do_memcpy(svo_ctx_t c, uint32_t *dst, uint32_t dstofs, const uint32_
 
 // The node pool is the only data the ray kernels re-read across frames; the warping kernels stream ~100 MB per frame
 // through the same L2.  Keep the pool resident: persisting-L2 carve-out + an access-policy window on the stream.
+static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes);
+void svo_pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes) { pin_octree_in_l2(c, oct, bytes); }
 static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes)
 {
     if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || getenv("SVO_NO_L2_PIN")) return;
@@ -846,3 +778,5 @@ extern "C" int svo_frame_idbuf_size(void)
     svo_copy_to_host(&v, c->last_idbuf, 4, 0);
     return v;
 }
+
+#include "svo_bands.inc"
