@@ -157,16 +157,17 @@ k_band_resolve_gather(const BandGatherArgs a)
         }
     } else {
         const int b = (int)ticket * kGatherBlocksPerCta + (warp >> 1);      // local block index
+        const bool active = b < nblocks;
+        const bool even = (res_x & 1) == 0;
         bool hole = false;
         int x = 0, y = 0;
         bool valid[4] = {false, false, false, false};
         size_t pp[2] = {0, 0};
-        if (b < nblocks) {
+        unsigned long long k[4] = {kKeyEmpty, kKeyEmpty, kKeyEmpty, kKeyEmpty};
+        if (active) {
             const int bx = b % nbx, by = m.global_brow(b / nbx);
             x = bx * 16 + (lane & 7) * 2;
             y = by * 16 + ((warp & 1) * 4 + (lane >> 3)) * 2;
-            unsigned long long k[4];
-            const bool even = (res_x & 1) == 0;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t p = (size_t)(y + r) * res_x + x;
@@ -176,10 +177,30 @@ k_band_resolve_gather(const BandGatherArgs a)
                     k[2 * r] = kk.x; k[2 * r + 1] = kk.y;
                 } else { k[2 * r] = key[p]; k[2 * r + 1] = key[p + 1]; }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) valid[i] = key_valid(k[i]);
+            hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
+        }
+        // aggregate published before the (possibly remote) gathers, as in k_resolve_gather
+        const unsigned mk = __ballot_sync(0xffffffffu, hole);
+        if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(mk);
+        if (tid == 0) resid_cta_s = 0;
+        __syncthreads();
+        uint32_t cta_total = 0, before_me = 0;
+#pragma unroll
+        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
+            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
+            if (i < (warp >> 1)) before_me += cnt;
+            cta_total += cnt;
+        }
+        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
+        const unsigned long long tag = (unsigned long long)a.epoch << 34;
+        if (tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+
+        if (active) {
             uint32_t col[4]; float4 pc[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                valid[i] = key_valid(k[i]);
                 col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid[i]) band_source(m, a.P, (uint32_t)k[i], n, col[i], pc[i]);
             }
@@ -204,45 +225,21 @@ k_band_resolve_gather(const BandGatherArgs a)
                 if (even) *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
                 else { dscreen[p] = out[0]; dscreen[p + 1] = out[1]; }
             }
-            hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
         }
-        const unsigned mk = __ballot_sync(0xffffffffu, hole);
-        if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(mk);
         unsigned int rflags = 0;
-        if (b < nblocks && !hole) {
+        if (active && !hole) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int px = x + (i & 1), py = y + (i >> 1);
                 if (!valid[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
             }
         }
-        if (tid == 0) resid_cta_s = 0;
-        __syncthreads();
         const unsigned int rcnt = (unsigned int)__popc(rflags);
         unsigned int rofs = 0;
         if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
         __syncthreads();
         if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
-        __syncthreads();
-        if (rflags) {
-            uint32_t *o = a.s.resid + resid_base_s + rofs;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
-        }
-        uint32_t cta_total = 0, before_me = 0;
-#pragma unroll
-        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
-            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
-            if (i < (warp >> 1)) before_me += cnt;
-            cta_total += cnt;
-        }
-        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
         if (warp == 0) {                                                    // decoupled look-back, as in k_resolve_gather
-            const unsigned long long tag = (unsigned long long)a.epoch << 34;
-            if (lane == 0) {
-                __threadfence();
-                atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
-            }
             uint32_t excl = 0;
             if (ticket > 0) {
                 int look = (int)ticket - 1;
@@ -263,16 +260,18 @@ k_band_resolve_gather(const BandGatherArgs a)
                     if (pm || look - 32 < 0) break;
                     look -= 32;
                 }
-                if (lane == 0) {
-                    __threadfence();
-                    atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
-                }
+                if (lane == 0) atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
             }
             if (lane == 0) cta_prefix_s = excl;
         }
         __syncthreads();
+        if (rflags) {
+            uint32_t *o = a.s.resid + resid_base_s + rofs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
+        }
         const uint32_t cta_prefix = cta_prefix_s;
-        if (b < nblocks) {
+        if (active) {
             const uint32_t ofs = cta_prefix + before_me;
             if ((warp & 1) == 0 && lane == 0) {
                 if (b > 0) a.idb[b] = my_block_cnt;

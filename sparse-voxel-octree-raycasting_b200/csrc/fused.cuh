@@ -139,16 +139,17 @@ k_resolve_gather(const GatherArgs a)
         }
     } else {
         const int b = (int)ticket * kGatherBlocksPerCta + (warp >> 1);
+        const bool active = b < nblocks;
+        const bool even = (res_x & 1) == 0;
         bool hole = false;
         int x = 0, y = 0;
         bool valid[4] = {false, false, false, false}, inr[4] = {false, false, false, false};
         size_t pp[2] = {0, 0};
-        if (b < nblocks) {
+        unsigned long long k[4] = {kKeyEmpty, kKeyEmpty, kKeyEmpty, kKeyEmpty};
+        if (active) {
             const int bx = b % nbx, by = b / nbx;
             x = bx * 16 + (lane & 7) * 2;
             y = by * 16 + ((warp & 1) * 4 + (lane >> 3)) * 2;
-            unsigned long long k[4];
-            const bool even = (res_x & 1) == 0;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t p = (size_t)(y + r) * res_x + x;
@@ -158,11 +159,32 @@ k_resolve_gather(const GatherArgs a)
                     k[2 * r] = kk.x; k[2 * r + 1] = kk.y;
                 } else { k[2 * r] = a.key[p]; k[2 * r + 1] = a.key[p + 1]; }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) valid[i] = key_valid(k[i]);
+            hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
+        }
+        // The hole counts depend on the keys alone: publish this CTA's aggregate for the look-back scan BEFORE the gathers,
+        // so the successors never wait for this CTA's memory traffic.
+        const unsigned m = __ballot_sync(0xffffffffu, hole);
+        if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(m);
+        if (tid == 0) resid_cta_s = 0;
+        __syncthreads();
+        uint32_t cta_total = 0, before_me = 0;
+#pragma unroll
+        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
+            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
+            if (i < (warp >> 1)) before_me += cnt;
+            cta_total += cnt;
+        }
+        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
+        const unsigned long long tag = (unsigned long long)a.epoch << 34;
+        if (tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+
+        if (active) {
             // all four gathers in flight before the first use
             uint32_t col[4]; float4 pc[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                valid[i] = key_valid(k[i]);
                 inr[i] = a.skip_tile && in_rect(a.tile, x + (i & 1), y + (i >> 1));
                 col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid[i]) {
@@ -193,48 +215,24 @@ k_resolve_gather(const GatherArgs a)
                 if (even && !inr[2 * r] && !inr[2 * r + 1]) *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
                 else { if (!inr[2 * r]) dscreen[p] = out[0]; if (!inr[2 * r + 1]) dscreen[p + 1] = out[1]; }
             }
-            hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hole);
-        if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(m);
         // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
         // global atomic per CTA (a single counter hit by every pixel would serialise in L2)
         unsigned int rflags = 0;
-        if (b < nblocks && !hole) {
+        if (active && !hole) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int px = x + (i & 1), py = y + (i >> 1);
                 if (!valid[i] && !inr[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
             }
         }
-        if (tid == 0) resid_cta_s = 0;
-        __syncthreads();
         const unsigned int rcnt = (unsigned int)__popc(rflags);
         unsigned int rofs = 0;
         if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
         __syncthreads();
         if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
-        __syncthreads();
-        if (rflags) {
-            uint32_t *o = a.s.resid + resid_base_s + rofs;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
-        }
-        uint32_t cta_total = 0, before_me = 0;
-#pragma unroll
-        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
-            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
-            if (i < (warp >> 1)) before_me += cnt;
-            cta_total += cnt;
-        }
-        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
         // decoupled look-back over the predecessors' aggregates (ticket order)
         if (warp == 0) {
-            const unsigned long long tag = (unsigned long long)a.epoch << 34;
-            if (lane == 0) {
-                __threadfence();
-                atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
-            }
             uint32_t excl = 0;
             if (ticket > 0) {
                 int look = (int)ticket - 1;
@@ -255,16 +253,18 @@ k_resolve_gather(const GatherArgs a)
                     if (pm || look - 32 < 0) break;
                     look -= 32;
                 }
-                if (lane == 0) {
-                    __threadfence();
-                    atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
-                }
+                if (lane == 0) atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
             }
             if (lane == 0) cta_prefix_s = excl;
         }
         __syncthreads();
+        if (rflags) {
+            uint32_t *o = a.s.resid + resid_base_s + rofs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
+        }
         const uint32_t cta_prefix = cta_prefix_s;
-        if (b < nblocks) {
+        if (active) {
             const uint32_t ofs = cta_prefix + before_me;
             if ((warp & 1) == 0 && lane == 0) {
                 if (b > 0) a.idb[b] = my_block_cnt;                         // raycast_counthole :273 (word 0 becomes the total)
