@@ -163,6 +163,96 @@ def octree_words_per_ray(octree, root, frames=(0, 40)):
     return l.value / max(1, r.value), i.value / max(1, r.value)
 
 
+def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, frames=48):
+    """BASELINE.json config 3: 3840x2160 on screen bands (stripes of --stripe-rows rows dealt round-robin to the ranks,
+    octree replicated): full raycasts (no exchange but the end-of-frame barrier and the colorized rows stored into rank
+    0's frame over NVLink) and the warped pipeline (reprojection by peer atomics).  Strong scaling: one image, all ranks."""
+    RX, RY = 3840, 2160
+    ocl, rc = svo.ocl, svo.raycast
+    db = svo.bands.DistributedBand(octree, root, RX, RY, local_rank, stripe_rows=args.stripe_rows, dist=dist)
+
+    def params(f):
+        rc.set_camera(*flythrough_pose(f))
+        return rc.prepare_params(RX, RY, f)
+
+    def fence():
+        db.band.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, items):
+        fence()
+        ocl.event_record(6)
+        for it in items:
+            fn(it)
+        ocl.event_record(7)
+        ms = ocl.event_elapsed_ms(6, 7)
+        fence()
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    P = [params(f) for f in range(4 + frames)]
+    for p in P[:3]:
+        db.band.raycast(p)
+    ray_ms = timed(db.band.raycast, P[4:4 + frames])
+    for p in P[:4]:                                   # frames 0 and 1 are full raycasts through the hole path
+        db.band.frame(p)
+    warp_ms = timed(db.band.frame, P[4:4 + frames])
+    out = {"ranks": world, "stripe_rows": db.band.lay["SR"], "scaling": "strong", "frames": frames,
+           "full_raycast_mrays_per_s": frames * RX * RY / (ray_ms * 1e-3) / 1e6, "full_raycast_ms": ray_ms / frames,
+           "warped_fps": frames / (warp_ms * 1e-3), "warped_ms": warp_ms / frames,
+           "exchange": "peer atomicMin / peer gather / halo rows / colorized rows over NVLink, flag barriers in peer memory; no NCCL"}
+    db.close()
+    return out
+
+
+def terrain14_bench(svo, args, frames=64):
+    """BASELINE.json config 4: fBm fractal terrain at OCTREE_DEPTH 14 (4096^2 columns of a 16384^3 world, 3-voxel shell),
+    the flythrough at 8x translation and 4x rotation speed (high hole fraction), 1920x1024, fused frame."""
+    rc, ocl = svo.raycast, svo.ocl
+    t0 = time.perf_counter()
+    vox = svo.scene.generate(kind=2, depth=14, size=4096, nblobs=0, seed=0x5EED)
+    octree, root, stats = svo.scene.build_octree_voxels(vox, depth=14)
+    vox.free()
+    build_s = time.perf_counter() - t0
+    rc.raycast_init(octree, root, max_w=RES_X, max_h=RES_Y, depth=14, mode=args.mode)
+    n = RES_X * RES_Y
+
+    def pose(f):
+        return ((8.0 + f * 8 * 0.2357, 440.0, 8.0 + f * 8 * 0.2357),
+                (0.6 + 0.1 * math.sin(2.0 * math.pi * f * 4 / 128.0), 0.8 + 4 * 0.005 * f, 0.0))
+
+    P = []
+    for f in range(4 + frames):
+        rc.set_camera(*pose(f))
+        P.append(rc.prepare_params(RES_X, RES_Y, f))
+    for p in P[:4]:
+        rc.draw_prepared(p, sync=False)
+    ocl.ocl_end_all_kernels()
+    holes = []
+    ocl.event_record(8)
+    for p in P[4:]:
+        rc.draw_prepared(p, sync=False)
+    ocl.event_record(9)
+    ms = ocl.event_elapsed_ms(8, 9)
+    ocl.ocl_end_all_kernels()
+    rc.reset_frames()
+    for p in P[:4 + 16]:                               # hole fraction of a few frames (needs a read-back each: untimed)
+        rc.draw_prepared(p, sync=True)
+        if p.frame >= 4:
+            holes.append(rc.idbuf_size() / n)
+    rc.set_camera(*pose(8))
+    ray_ms = rc.full_raycast_ms(RES_X, RES_Y)
+    rc.raycast_exit()
+    return {"warped_fps": frames / (ms * 1e-3), "ms_per_frame": ms / frames, "hole_fraction_mean": float(np.mean(holes)),
+            "full_raycast_mrays_per_s": n / (ray_ms * 1e-3) / 1e6, "octree_mb": round(octree.nbytes / 2 ** 20, 1),
+            "voxels": stats["num_voxels"], "depth": 14, "host_build_s": round(build_s, 1),
+            "config": "fBm terrain 4096x4096 columns at depth 14, camera 8x translation / 4x rotation of the config-2 path"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,6 +261,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-frames", type=int, default=32)
+    ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (bands at 3840x2160, 64-camera batch, depth-14 terrain)")
     ap.add_argument("--mode", default="fused", choices=["fused", "pingpong"],
                     help="fused: every buffer as the reference leaves it (cache copy kept); pingpong: SVO_FRAME_PINGPONG, no cache copy")
     args = ap.parse_args()
@@ -201,6 +293,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -290,13 +383,27 @@ def main():
     prof = ocl.profile_all()
     ocl.profile_enable(False)
 
+    # ---- BASELINE.json config 5: 64 cameras view-parallel (full raycast each), cameras dealt round-robin to the ranks ----
+    cams64 = [flythrough_pose(4 * i) for i in range(64)][rank::world]
+    for pose_ in cams64[:2]:
+        rc.set_camera(*pose_)
+        rc.full_raycast_enqueue(RES_X, RES_Y)
+    sync_all()
+    ocl.event_record(4)
+    for pose_ in cams64:
+        rc.set_camera(*pose_)
+        rc.full_raycast_enqueue(RES_X, RES_Y)
+    ocl.event_record(5)
+    cams_ms = ocl.event_elapsed_ms(4, 5)
+    sync_all()
+
     # ---- max over ranks ----
-    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t = torch.tensor([ms, e2e_s * 1000.0, cams_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     mr = torch.tensor([mrays], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(mr, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, cams_ms_max = float(t[0]), float(t[1]), float(t[2])
     fps = world * args.steps / (ms_max * 1e-3)
     e2e_fps = world * args.steps / (e2e_ms_max * 1e-3)
 
@@ -352,8 +459,17 @@ def main():
             r = cpu_arm(octree, root, steps=24, warmup=args.warmup, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["full_raycast_mrays_per_s"] = r["full_raycast_mrays_per_s"]
-        print(json.dumps(line))
     rc.raycast_exit()
+    extras = {}
+    if not args.no_extras:
+        extras["view_parallel_64_cameras"] = {"grays_per_s": 64 * n / (cams_ms_max * 1e-3) / 1e9, "ms": cams_ms_max,
+                                              "config": "64 poses of the flythrough (every 4th frame), full raycast 1920x1024 each, dealt round-robin to the ranks, no communication"}
+        extras["bands_3840x2160"] = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args)
+        if world == 1:
+            extras["terrain_depth14"] = terrain14_bench(svo, args)
+    if rank == 0:
+        line.update(extras)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -249,10 +249,9 @@ class DistributedBand:
     """This process' band of a torchrun job: rank r drives GPU ``device`` and owns the stripes r, r+G, ..."""
 
     def __init__(self, octree_words, octree_root, res_x, res_y, device, stripe_rows=0, depth=11, dist=None):
-        if dist is None:
-            import torch.distributed as dist
+        """dist: an initialised torch.distributed module, or None for a single-process (world 1) run."""
         self.dist = dist
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
         ocl.ocl_init(device)
         ocl.set_octree_depth(depth)
         octree_words = np.ascontiguousarray(octree_words, dtype=np.uint32)

@@ -286,6 +286,24 @@ def full_raycast_ms(res_x, res_y, repeats=5):
     return float(np.median(times))
 
 
+def full_raycast_enqueue(res_x, res_y):
+    """raycast_fine_2 over the whole screen for the camera set with set_camera(); asynchronous (view-parallel batches)."""
+    m = rotation_matrix(S.rot)
+    pos = wrap_pos(S.pos)
+    v0 = np.array([pos[0], pos[1], pos[2], 1.0], dtype=np.float32)
+    dead = (0.0, 0.0, 0.0, 0.0)
+    ocl.ocl_begin(_kernel("raycast_fine_2"), res_x, res_y, 16, 16)
+    for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree):
+        ocl.ocl_param(a)
+    ocl.ocl_param(C.c_uint32(S.octree_root_normal))
+    for a in (res_x, res_y, 0, 0, 0):
+        ocl.ocl_param(C.c_int(a))
+    for a in (dead, dead, dead, dead, v0, m[:, 0].copy(), m[:, 1].copy(), m[:, 2].copy()):
+        ocl.ocl_param(a)
+    ocl.ocl_param(C.c_float(1.0)); ocl.ocl_param(C.c_float(1.0))
+    ocl.ocl_end()
+
+
 def idbuf_size():
     return ocl.frame_idbuf_size() if S.mode in ("fused", "pingpong") else S.idbuf_size
 

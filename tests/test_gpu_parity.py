@@ -298,3 +298,39 @@ def test_errors_are_reported(svo):
     svo.ocl_param(C.c_int(1))
     with pytest.raises(RuntimeError):
         svo.ocl_end()                                # wrong argument count / sizes
+
+
+def test_frame_sequence_depth_14(svo, orc):
+    """OCTREE_DEPTH 14 (BASELINE.json config 4; a compile-time constant of the reference, a context setting here):
+    full pipeline on a small fractal-terrain patch of a 16384^3 world, every buffer bit-exact against the oracle built
+    with the same depth."""
+    t = scenes.terrain(192, 6000, 9000, height=260, base=8000, seed=5)
+    orc.lib.orc_set_depth(14)
+    try:
+        octree, root = orc.build_octree(*t)
+        rx, ry = 320, 192
+        n = rx * ry
+        O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4, depth=14)
+        rc = svo.raycast
+        svo.ocl_exit()
+        rc.raycast_init(octree, root, max_w=rx, max_h=ry, depth=14, mode="fused")
+        try:
+            for f in range(8):
+                # world units = voxels / 8: look down at the patch from above, moving fast (high hole fraction)
+                pos, rot = (6000 / 8 + 6 + 0.6 * f, 8000 / 8 + 60, 9000 / 8 + 4 + 0.4 * f), (0.9, 0.6 + 0.03 * f, 0.0)
+                O.draw(pos, rot)
+                rc.set_camera(pos, rot)
+                rc.raycast_draw(rx, ry)
+                screen, back, idb = rc.read_buffers(rx, ry)
+                assert rc.idbuf_size() == O.idbuf_size, f"frame {f}"
+                assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"frame {f} ids"
+                assert np.array_equal(screen, O.screen[:4 * n]), f"frame {f} colour"
+                assert np.array_equal(back.view(np.uint32), O.back[:16 * n].view(np.uint32)), f"frame {f} xyz"
+                assert np.array_equal(rc.read_frame(rx, ry).ravel(), O.tex), f"frame {f} tex"
+            hit = (O.screen[:n] & 0xff) != 0
+            assert 0.05 < hit.mean(), "the camera does not see the terrain patch"
+        finally:
+            rc.raycast_exit()
+            svo.ocl_init(0)
+    finally:
+        orc.lib.orc_set_depth(11)
