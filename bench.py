@@ -329,9 +329,11 @@ def main():
     sampler.start()
     launches0 = svo.launch_count()
     ocl.event_record(0)
+    t_enq = time.perf_counter()
     for f in range(args.warmup, total):
         rc.draw_prepared(P[f], sync=False)
     ocl.event_record(1)
+    host_enqueue_ms = (time.perf_counter() - t_enq) * 1000.0 / args.steps   # CPU time to issue one frame (launch-bound check)
     ms = ocl.event_elapsed_ms(0, 1)
     sync_all()
     launches = svo.launch_count() - launches0
@@ -442,7 +444,7 @@ def main():
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 4,
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum},
-                "gpu_launches": launches, "clocks": sampler.summary(),
+                "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom),

@@ -32,6 +32,11 @@ struct svo_ctx_s {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
     cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
+    cudaEvent_t ev_copy_done = nullptr, ev_patch_done = nullptr;
+    svo::PatchList patch = {nullptr, nullptr};   // gap-filter results of the last fused frame, applied on stream2
+    size_t patch_pixels = 0;
+    bool patch_event_valid = false;
+    bool patch_pending = false;             // stream must wait for ev_patch_done before it touches buffer 0 again
     int last_slot = 0;                      // slot the last fused frame rendered into
     bool have_frame = false;
     int num_sms = 148;

@@ -37,15 +37,18 @@ __device__ __forceinline__ uint32_t popc8(uint32_t v) { return __popc(v & 0xffu)
 __device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct, uint32_t node, uint32_t before,
                                                 uint32_t &local_root, uint32_t child, uint32_t child_test, int rekursion)
 {
+    // word indices are summed in 32 bits (the pool is < 2^32 words): one IMAD.WIDE per load instead of a 64-bit chain
     uint32_t n = node >> 9, nadd = child;
     if (node & 256u) {
         if (!(before & 256u)) { local_root = n << 6; n = 0; }
         n += local_root;
         nadd = popc8(node & ((child_test << 1) - 1u));
-        if (rekursion == 2) return ((ldg(oct + n + (nadd >> 2)) >> ((nadd & 3u) << 3)) & 255u) + 256u + (nadd << 9);
-        if (rekursion == 1) return 0u;
+        if (rekursion <= 2) {                                             // the two byte-packed levels, once per ray
+            if (rekursion == 1) return 0u;
+            return ((ldg(oct + (n + (nadd >> 2))) >> ((nadd & 3u) << 3)) & 255u) + 256u + (nadd << 9);
+        }
     }
-    return ldg(oct + n + nadd);
+    return ldg(oct + (n + nadd));
 }
 
 // sum of popcounts of bytes 1..n-1 of a byte-packed record (the loops at kernel/kernel.cl:82-85,104-107).
@@ -172,7 +175,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
             }
             if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }    // :209
         }
-        if ((x0ry & (2 * kDepthAnd + 2)) || !--guard) break;           // :211 the ray left the world through y
+        if ((x0ry & kScaleMax) != 0 || !--guard) break;                // :211 the ray left the world through y
     }
 
     if (sign_xyz & 1) px = (float)kScaleMax - px;

@@ -39,6 +39,15 @@ static svo_ctx_t need_ctx()
 }
 svo_ctx_t svo_need_ctx() { return need_ctx(); }
 
+// The fused frame writes its gap-filter results into buffer 0 on the second stream (k_apply_patches), off the critical
+// path.  Anything issued on the main stream that may touch buffer 0 is ordered behind that first.
+static void join_patches(svo_ctx_t c)
+{
+    if (!c->patch_pending) return;
+    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_patch_done, 0));
+    c->patch_pending = false;
+}
+
 extern "C" int svo_device_count(void)
 {
     int n = 0;
@@ -67,6 +76,8 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_patch_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     return c;
@@ -85,6 +96,9 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
+    cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_patch_done);
+    if (c->patch.items) cudaFree(c->patch.items);
+    if (c->patch.count) cudaFree(c->patch.count);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (auto &e : c->present_ready) if (e) cudaEventDestroy(e);
@@ -158,6 +172,7 @@ extern "C" void svo_copy_to_host(void *dst, svo_mem_t src, size_t size, size_t s
     svo_ctx_t c = need_ctx();
     if (!c) return;
     if (!src || srcofs + size > src->bytes) { svo_fail(-104, "svo_copy_to_host out of range"); return; }
+    join_patches(c);
     CU_CHECK(cudaMemcpyAsync(dst, (const char *)src->dptr + srcofs, size, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
 }
@@ -167,6 +182,7 @@ extern "C" void svo_copy_to_device(svo_mem_t dst, size_t dstofs, const void *src
     svo_ctx_t c = need_ctx();
     if (!c) return;
     if (!dst || dstofs + size > dst->bytes) { svo_fail(-105, "svo_copy_to_device out of range"); return; }
+    join_patches(c);
     CU_CHECK(cudaMemcpyAsync((char *)dst->dptr + dstofs, src, size, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
 }
@@ -185,6 +201,7 @@ extern "C" void svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, si
     svo_ctx_t c = need_ctx();
     if (!c) return;
     if (!src || srcofs + size > src->bytes) { svo_fail(-104, "svo_copy_to_host_async out of range"); return; }
+    join_patches(c);
     CU_CHECK(cudaMemcpyAsync(dst, (const char *)src->dptr + srcofs, size, cudaMemcpyDeviceToHost, c->stream));
 }
 
@@ -205,6 +222,7 @@ extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, in
     }
     CU_CHECK(cudaEventRecord(c->present_ready[slot], c->stream));
     CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->present_ready[slot], 0));
+    if (c->patch_event_valid) CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_patch_done, 0));   // the gap filter's pixels
     CU_CHECK(cudaMemcpyAsync(host_dst, src->dptr, size, cudaMemcpyDeviceToHost, c->copy_stream));
     CU_CHECK(cudaEventRecord(c->present_done[slot], c->copy_stream));
 }
@@ -472,6 +490,7 @@ extern "C" void svo_memcpy(svo_mem_t dst, uint32_t dstofs, svo_mem_t src, uint32
     svo_ctx_t c = need_ctx();
     if (!c) return;
     if (!dst || !src) { svo_fail(-106, "svo_memcpy: null buffer"); return; }
+    join_patches(c);
     srcofs /= 4; dstofs /= 4; size /= 4;
     uint32_t n = (uint32_t)svo_round_up(256, (int)size);
     n = clamp_words(dst, dstofs, n);
@@ -484,6 +503,7 @@ extern "C" void svo_memset(svo_mem_t dst, uint32_t dstofs, uint32_t val, uint32_
     svo_ctx_t c = need_ctx();
     if (!c) return;
     if (!dst) { svo_fail(-107, "svo_memset: null buffer"); return; }
+    join_patches(c);
     dstofs /= 4; size /= 4;
     uint32_t n = clamp_words(dst, dstofs, (uint32_t)svo_round_up(256, (int)size));
     do_memset(c, (uint32_t *)dst->dptr, dstofs, val, n);
@@ -583,6 +603,7 @@ extern "C" void svo_end(void)
         }
     }
     const int gx = (int)g_global[0], gy = (int)g_global[1];
+    join_patches(c);
     switch (k->id) {
     case K_MEMSET: {
         svo_mem_t m = arg<svo_mem_t>(0);
@@ -690,7 +711,13 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
 
     const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     ensure_key(c, n);
-    ensure_fused_scratch(c, ncta + 64, n);
+    ensure_fused_scratch(c, ncta + 64, 1);
+    if (c->patch_pixels < n) {
+        if (c->patch.items) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaFree(c->patch.items)); }
+        CU_CHECK(cudaMalloc(&c->patch.items, (size_t)n * sizeof(uint2)));
+        if (!c->patch.count) { CU_CHECK(cudaMalloc(&c->patch.count, 8)); CU_CHECK(cudaMemsetAsync(c->patch.count, 0, 8, c->stream)); }
+        c->patch_pixels = n;
+    }
     const bool strips = (res_x % 16) || (res_y % 16);
     const bool pingpong = (p->flags & SVO_FRAME_PINGPONG) != 0;
     // buffer roles (slots of the reference's 4-buffer arrays)
@@ -709,9 +736,9 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const bool overlap = !getenv("SVO_NO_OVERLAP");
     c->epoch = (c->epoch + 1) & 0x3fffffffu;
     if (c->epoch == 0) c->epoch = 2;                                       // keeps the parity sequence alternating
-    c->fs.resid_count = c->fs.counters + 2 + (c->epoch & 1u);
-    unsigned int *next_resid_count = c->fs.counters + 2 + ((c->epoch + 1) & 1u);
 
+    // ping-pong: the previous frame's gap filter still reads the slot this frame's scatter is about to invalidate pixels in
+    if (pingpong) join_patches(c);
     if (frame < 2) {                                                       // :150-154 (the destination is rewritten below)
         if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
         else do_memset(c, screen, n, kHole, n * 3);
@@ -733,9 +760,10 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     {   // :177-198 source buffers in ascending offset = the reference's launch order
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = (unsigned int)src_count * n;
-        k_proj_scatter2<<<bw_grid(c, nsrc, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, next_resid_count, res_x, res_y,
+        k_proj_scatter2<<<bw_grid(c, nsrc, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, nullptr, res_x, res_y,
                                                                         (unsigned int)src_first * n, nsrc, pc);
     }
+    join_patches(c);                                                       // the previous frame's filtered words are in buffer 0
     {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
         LAUNCH(c, "k_resolve_gather");
         GatherArgs ga = {screen, back, c->key, idb, c->fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc};
@@ -750,18 +778,28 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     if (overlap) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
     else launch_tile(c->stream);
     uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
-    if (!pingpong || tex) {   // :394-405 cache copy (target 2) + :429-437 colorize
-        LAUNCH(c, "k_copy_colorize");
-        k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 4, 256, 8), 256, 0, c->stream>>>(
-            dscreen, reinterpret_cast<const float4 *>(dback), pingpong ? nullptr : screen + 2 * (size_t)n,
-            pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
-    }
-    if (!pingpong || tex) {   // :411-422 gap filter on the listed hole pixels, reading the pre-filter image
-        LAUNCH(c, "k_fill_list");
-        // exact: snapshot = the copy in buffer 2, words past the image = what follows buffer 0 (buffer 1);
-        // ping-pong: the destination slot itself (never written here) and what follows it
-        SnapView view = {pingpong ? dscreen : screen + 2 * (size_t)n, dscreen, (int)n};
-        k_fill_list<<<c->num_sms * 2, 256, 0, c->stream>>>(view, pingpong ? nullptr : screen, tex, c->fs, res_x);
+    if (!pingpong || tex) {
+        {   // :394-405 cache copy (target 2) + :429-437 colorize, one streaming pass
+            LAUNCH(c, "k_copy_colorize");
+            k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
+                dscreen, reinterpret_cast<const float4 *>(dback), pingpong ? nullptr : screen + 2 * (size_t)n,
+                pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, res_x, res_y, c->patch);
+        }
+        // :411-422 gap filter on the listed hole pixels: second stream, nobody on the main stream waits for it before the
+        // next frame's resolve pass (join_patches)
+        CU_CHECK(cudaEventRecord(c->ev_copy_done, c->stream));
+        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_copy_done, 0));
+        {
+            LAUNCH_ON(c, "k_fill_compute", c->stream2);
+            k_fill_compute<<<c->num_sms * 2, 256, 0, c->stream2>>>(dscreen, tex, c->patch, res_x);
+        }
+        {
+            LAUNCH_ON(c, "k_apply_patches", c->stream2);
+            k_apply_patches<<<64, 256, 0, c->stream2>>>(pingpong ? nullptr : dscreen, c->patch);
+        }
+        CU_CHECK(cudaEventRecord(c->ev_patch_done, c->stream2));
+        c->patch_pending = true;
+        c->patch_event_valid = true;
     }
     c->last_slot = dst_slot;
     c->have_frame = true;

@@ -334,3 +334,63 @@ def test_frame_sequence_depth_14(svo, orc):
             svo.ocl_init(0)
     finally:
         orc.lib.orc_set_depth(11)
+
+
+EDGE_SCENES = {
+    "dense_cube": lambda: scenes.cube(1000, 1000, 1000, 40),                      # every byte-packed record full (k = 8)
+    "sparse_cloud": lambda: scenes.random_cloud(4000, 900, 1200, 5),              # mostly single-voxel records (k = 1)
+    "single_voxel": lambda: scenes.single_voxel(1024, 1024, 1024),
+    "block_edges": lambda: scenes.concat(scenes.cube(1023 - 4, 1023 - 4, 1023 - 4, 10), scenes.single_voxel(1087, 1024, 1088)),
+    "duplicates": scenes.duplicates,
+}
+EDGE_POSES = [((127.0, 128.5, 120.0), (0.05, 0.02, 0.0)),         # in front of the centre, nearly axis-aligned rays
+              ((128.0, 128.0, 128.0), (1.5707963, 0.0, 0.0)),     # integer camera position, looking straight along an axis
+              ((125.3, 135.2, 126.1), (0.9, 2.4, 0.3)),           # oblique, rolled
+              ((-3.0, 300.0, 260.5), (0.7, 0.8, 0.0))]            # outside the world: position wraps (src/raycast.h:136-145)
+
+
+@pytest.mark.parametrize("scene", sorted(EDGE_SCENES))
+def test_raycast_edge_scenes(svo, orc, scene):
+    """Octree edge cases (full / single-entry byte-packed records, voxels on block boundaries, duplicates) under
+    axis-aligned, integer-position, rolled and wrapped cameras: raycast_fine_2 over the screen and raycast_holes over a
+    ragged id list (length not a multiple of the work-group size), hit words and positions bit-exact."""
+    octree, root = orc.build_octree(*EDGE_SCENES[scene]())
+    rx, ry = 160, 96
+    n, nb = rx * ry, (rx // 16) * (ry // 16)
+    mo = svo.ocl_malloc(octree.nbytes, octree)
+    dead = (0, 0, 0, 0)
+    rng = np.random.RandomState(11)
+    for pose in EDGE_POSES:
+        cam = ofr.camera_args(*pose)
+        screen = np.full(4 * n, HOLE, dtype=np.uint32)
+        back = np.zeros(16 * n, dtype=np.float32)
+        orc.raycast_fine_2(screen, back, octree, root, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], gx=rx, gy=ry, threads=4)
+        ms = svo.ocl_malloc(4 * n * 4, np.full(4 * n, HOLE, dtype=np.uint32))
+        mb = svo.ocl_malloc(16 * n * 4, np.zeros(16 * n, dtype=np.float32))
+        launch(svo, "raycast_fine_2", rx, ry, 16, 16,
+               [ms, mb, mo, C.c_uint32(root), i32(rx), i32(ry), i32(0), i32(0), i32(0), dead, dead, dead, dead,
+                cam["v0"], *cam["cols"], C.c_float(1.0), C.c_float(1.0)])
+        assert np.array_equal(ms.to_numpy(), screen), (scene, pose)
+        assert np.array_equal(mb.to_numpy(np.uint32), back.view(np.uint32)), (scene, pose)
+        # raycast_holes over a ragged list of 1003 random pixels (and an empty list: no launch, src/raycast.h:330)
+        for count in (1003, 0):
+            ids = np.zeros(2 * nb + n, dtype=np.uint32)
+            px = rng.randint(0, rx, size=count).astype(np.uint32)
+            py = rng.randint(0, ry, size=count).astype(np.uint32)
+            ids[2 * nb:2 * nb + count] = px | (py << 16)
+            ids[0] = count
+            s2 = np.full(4 * n, HOLE, dtype=np.uint32)
+            b2 = np.zeros(16 * n, dtype=np.float32)
+            mi = svo.ocl_malloc(ids.nbytes, ids)
+            svo.ocl_copy_to_device(ms, 0, s2)
+            svo.ocl_copy_to_device(mb, 0, b2)
+            if count:
+                orc.raycast_holes(s2, b2, octree, ids, root, rx, ry, 0, count, cam["v0"], *cam["cols"], threads=4)
+                launch(svo, "raycast_holes", count, 1, 256, 1,
+                       [ms, mb, mo, None, None, None, mi, C.c_uint32(root), i32(rx), i32(ry), i32(0), i32(count),
+                        dead, dead, dead, dead, cam["v0"], *cam["cols"], C.c_float(1.0), C.c_float(1.0)])
+            assert np.array_equal(ms.to_numpy(), s2), (scene, pose, count)
+            assert np.array_equal(mb.to_numpy(np.uint32), b2.view(np.uint32)), (scene, pose, count)
+            mi.free()
+        ms.free(); mb.free()
+    mo.free()
