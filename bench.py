@@ -427,7 +427,7 @@ def main():
                "k_resolve_gather": 8.0 * n + 20.0 * W + 20.0 * W + 4.0 * (n - W) + 8.0 * W + 4.0 * H,   # keys in, gather, dest out, hole words, re-arm, ids
                "k_rays_tile": (4.0 * L + 16.0) * tile_rays, "k_rays_holes": (4.0 * L + 20.0) * H,
                "k_copy_colorize": (44.0 if args.mode == "fused" else 8.0) * n,    # 20N in, 20N out, 4N image
-               "k_fill_list": 8.0 * resid_px}
+               "k_fill_compute": 28.0 * resid_px, "k_apply_patches": 12.0 * resid_px}
         d_ms, d_cnt = prof[dom]
         avg_ms = d_ms / max(1, d_cnt)
         achieved = alg.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9

@@ -81,6 +81,7 @@ void   svo_profile_enable(int on);
 void   svo_profile_reset(void);
 int    svo_profile_get(const char *cuda_kernel_name, double *total_ms, uint64_t *launches);
 int    svo_profile_names(char *buf, size_t bufsize);        /* newline-separated kernel names seen so far */
+int    svo_profile_timeline(char *buf, size_t bufsize);     /* "name start_us end_us" per launch of the last batch (all streams) */
 /* page-locked host memory for the headless framebuffer readback */
 void  *svo_host_alloc(size_t bytes);
 void   svo_host_free(void *p);

@@ -32,11 +32,14 @@ struct svo_ctx_s {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
     cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
-    cudaEvent_t ev_copy_done = nullptr, ev_patch_done = nullptr;
-    svo::PatchList patch = {nullptr, nullptr};   // gap-filter results of the last fused frame, applied on stream2
+    cudaEvent_t ev_copy_done = nullptr, ev_fill_done = nullptr;
+    svo::PatchList patch = {nullptr};       // gap-filter results of the last fused frame (k_fill_list on stream2)
+    unsigned int *patch_count = nullptr;    // the residual-hole counter and list they belong to
+    uint32_t *patch_resid = nullptr;
     size_t patch_pixels = 0;
-    bool patch_event_valid = false;
-    bool patch_pending = false;             // stream must wait for ev_patch_done before it touches buffer 0 again
+    bool fill_event_valid = false;          // ev_fill_done has been recorded at least once
+    bool fill_outstanding = false;          // the main stream has not yet been ordered behind the last k_fill_compute
+    uint32_t *patch_target = nullptr;       // != nullptr: the last frame's filtered words are not yet in buffer 0 (flush_patches)
     int last_slot = 0;                      // slot the last fused frame rendered into
     bool have_frame = false;
     int num_sms = 148;
@@ -61,6 +64,8 @@ struct svo_ctx_s {
     std::vector<ProfRec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     std::map<std::string, std::pair<double, uint64_t>> prof_acc;
+    struct TimelineRec { const char *name; float start_ms, end_ms; };
+    std::vector<TimelineRec> timeline;      // last flushed batch, relative to its first launch (svo_profile_timeline)
 };
 
 svo_ctx_t svo_need_ctx();

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256)
 k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int nslots, ProjCam c)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
-    uint32_t *__restrict__ screen = P.screen[m.rank];
+    // (the reference's "source leaves the view -> hole" store has no reader inside the frame, see k_proj_scatter2)
+    const uint32_t *__restrict__ screen = P.screen[m.rank];
     const float *__restrict__ back = P.back[m.rank];
     const unsigned int n = (unsigned int)m.res_x * m.res_y, nloc = (unsigned int)m.local_rows * m.res_x;
     bool remote = false;
@@ -87,7 +88,7 @@ k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_cou
             if (col == kHole) continue;
             const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4);
             int sx, sy; float phz;
-            if (!proj_point_fast(c, pc.x, pc.y, pc.z, m.res_x, m.res_y, sx, sy, phz)) { screen[srcofs] = kHole; continue; }
+            if (!proj_point_fast(c, pc.x, pc.y, pc.z, m.res_x, m.res_y, sx, sy, phz)) continue;
             const int o = m.owner(sy);
             remote |= o != m.rank;
             atomicMin(P.key[o] + (size_t)sy * m.res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);

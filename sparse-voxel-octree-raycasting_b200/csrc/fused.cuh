@@ -9,10 +9,12 @@
 //   k_rays_tile       raycast_fine_2 tile refresh (:361-387); independent of the reprojection, so it runs on a second
 //                     stream concurrently with the two kernels above
 //   k_rays_holes      raycast_holes (:332-359); idbuf_size is read on the device
-//   k_copy_colorize   cache copy (:394-405) + raycast_colorize (:429-437), pure streaming; lists the hole pixels it sees
-//   k_fill_compute    raycast_fillhole2 (:411-422) on the listed pixels, snapshot semantics: reads the unmodified frame,
-//   k_apply_patches   writes the colorized image at once and buffer 0 in a second launch -- both on the second stream, off
-//                     the critical path of the next frame (which does not touch buffer 0 before its resolve pass)
+//   k_copy_colorize   cache copy (:394-405) + raycast_colorize (:429-437), pure streaming
+//   k_fill_list       raycast_fillhole2 (:411-422), snapshot semantics, on the listed hole pixels only: reads the cache copy
+//                     just made, writes the filtered word to the colorized image and keeps it; second stream, off the
+//                     critical path of the next frame
+//   k_apply_patches   the filter's in-place write into buffer 0, issued only when the host can observe buffer 0 before
+//                     the next frame rewrites it (sync, read-back, launch-API use)
 //
 // Buffer roles are parameters (slot = buffer index in the reference's 4-buffer arrays):
 //   exact mode      sources = slots 1 and 2, destination = slot 0, copy target = slot 2: every buffer ends the frame
@@ -27,14 +29,13 @@ namespace svo {
 
 struct FusedScratch {
     unsigned long long *scan_state;   // per CTA ticket: epoch<<34 | flag<<32 | value
-    unsigned int *counters;           // [0] ticket, [1] done, [2],[3] residual-hole counts (alternating frames)
+    unsigned int *counters;           // [0] ticket, [1] done, [4..7] residual-hole counts (rotating over 4 frames)
     uint32_t *resid;                  // pixel offsets of the hole pixels left for the gap filter
-    unsigned int *resid_count;        // this frame's counter (&counters[2 + parity])
+    unsigned int *resid_count;        // this frame's counter
 };
 
-struct PatchList {                    // gap-filter results waiting to be written into buffer 0
-    uint2 *items;                     // (pixel offset, filtered word)
-    unsigned int *count;              // [0] entries, [1] CTAs of k_apply_patches that have read it
+struct PatchList {                    // gap-filter results: filtered word per entry of the residual-hole list
+    uint32_t *value;                  // value[i] belongs to pixel resid[i]; kHole = nothing within reach
 };
 
 struct Rect { int x0, y0, x1, y1; };  // tile-refresh rectangle [x0,x1) x [y0,y1) in pixels
@@ -68,22 +69,24 @@ __device__ __forceinline__ bool proj_point_fast(const ProjCam &c, float pcx, flo
 }
 
 // sources: `nsrc` pixels starting at pixel offset `src0` (exact mode: buffers 1 and 2 = 2N pixels from N; ascending
-// offset is the launch order of the reference, which is what breaks depth ties)
+// offset is the launch order of the reference, which is what breaks depth ties).
+// The reference also turns a source pixel that leaves the view into a hole (kernel.cl:559-562).  Inside the frame that
+// store has no reader: buffer 1 is all holes anyway, buffer 2 is overwritten by the cache copy at the end of the frame
+// (ping-pong: the slot is rewritten before it is read again), and the resolve pass only gathers sources that produced a
+// key.  It is therefore not issued here (the launch-by-launch raycast_proj of warp.cuh does it), which makes this kernel
+// read-only on the cache.  One source per thread, short-lived CTAs: launches of the second stream slip in between.
 __global__ void __launch_bounds__(256)
-k_proj_scatter2(uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
-                unsigned int *__restrict__ next_resid_count, int res_x, int res_y, unsigned int src0, unsigned int nsrc, ProjCam c)
+k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
+                int res_x, int res_y, unsigned int src0, unsigned int nsrc, ProjCam c)
 {
-    // re-arm the NEXT frame's gap-filter counter (this frame's may already be in use by the concurrent tile rays)
-    if (next_resid_count && blockIdx.x == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
-    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < nsrc; q += gridDim.x * blockDim.x) {
-        const uint32_t srcofs = q + src0;
-        const uint32_t col = screen[srcofs];
-        if (col == kHole) continue;
-        const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4);
-        int sx, sy; float phz;
-        if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) { screen[srcofs] = kHole; continue; }
-        atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);
-    }
+    const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nsrc) return;
+    const uint32_t srcofs = q + src0;
+    if (__ldg(screen + srcofs) == kHole) return;
+    const float4 pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+    int sx, sy; float phz;
+    if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) return;
+    atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -95,6 +98,7 @@ struct GatherArgs {
     unsigned int dst0;        // pixel offset of the destination slot
     Rect tile; int skip_tile; // tile rays run concurrently: leave colour / xyz of the tile rectangle to them
     ProjCam c;
+    unsigned int *next_resid_count;
 };
 
 // The destination was (logically) just cleared to holes, so a candidate is accepted iff its sz is below 0xffffff00
@@ -107,6 +111,7 @@ k_resolve_gather(const GatherArgs a)
     __shared__ unsigned int ticket_s;
     __shared__ uint32_t warp_cnt[8];
     __shared__ uint32_t cta_prefix_s;
+    __shared__ unsigned int resid_cta_s, resid_base_s;
     const int res_x = a.res_x, res_y = a.res_y;
     const int nbx = res_x / 16, nby = res_y / 16, nblocks = nbx * nby;
     const int ncta = (nblocks + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
@@ -116,6 +121,7 @@ k_resolve_gather(const GatherArgs a)
     if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
     __syncthreads();
     const unsigned int ticket = ticket_s;
+    if (ticket == 0 && tid == 0) a.next_resid_count[0] = 0;   // re-arm the counter used two frames from now
 
     if (ticket >= (unsigned)ncta) {
         // pixels outside the whole 16x16 blocks (right / bottom strips when the resolution is not a multiple of 16):
@@ -140,6 +146,7 @@ k_resolve_gather(const GatherArgs a)
                 else { dscreen[p] = (uint32_t)(k >> 32) + (col & 255u); *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz); }
             } else if (!inr) {
                 dscreen[p] = kHole;
+                if (x > 1 && y > 1 && x < res_x - 1 && y < res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
             }
         }
     } else {
@@ -172,6 +179,7 @@ k_resolve_gather(const GatherArgs a)
         // so the successors never wait for this CTA's memory traffic.
         const unsigned m = __ballot_sync(0xffffffffu, hole);
         if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(m);
+        if (tid == 0) resid_cta_s = 0;
         __syncthreads();
         uint32_t cta_total = 0, before_me = 0;
 #pragma unroll
@@ -220,6 +228,21 @@ k_resolve_gather(const GatherArgs a)
                 else { if (!inr[2 * r]) dscreen[p] = out[0]; if (!inr[2 * r + 1]) dscreen[p + 1] = out[1]; }
             }
         }
+        // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
+        // global atomic per CTA (a single counter hit by every pixel would serialise in L2)
+        unsigned int rflags = 0;
+        if (active && !hole) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int px = x + (i & 1), py = y + (i >> 1);
+                if (!valid[i] && !inr[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
+            }
+        }
+        const unsigned int rcnt = (unsigned int)__popc(rflags);
+        unsigned int rofs = 0;
+        if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
+        __syncthreads();
+        if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
         // decoupled look-back over the predecessors' aggregates (ticket order)
         if (warp == 0) {
             uint32_t excl = 0;
@@ -247,6 +270,11 @@ k_resolve_gather(const GatherArgs a)
             if (lane == 0) cta_prefix_s = excl;
         }
         __syncthreads();
+        if (rflags) {
+            uint32_t *o = a.s.resid + resid_base_s + rofs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
+        }
         const uint32_t cta_prefix = cta_prefix_s;
         if (active) {
             const uint32_t ofs = cta_prefix + before_me;
@@ -282,20 +310,21 @@ constexpr int kRaysBlock = 64;          // small CTAs: a short ray list still la
 template <int D>
 __global__ void __launch_bounds__(kRaysBlock)
 k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
-             const uint32_t *__restrict__ idb, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs)
+             const uint32_t *__restrict__ idb, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs, int smax)
 {
     __shared__ uint32_t stack[(D + 1) * kRaysBlock];
     const int idsize = (res_x / 16) * (res_y / 16);
     const long long total = (long long)idb[0];
     const long long nthreads = (long long)gridDim.x * kRaysBlock;
-    const int S = total * 4 <= nthreads ? 4 : total * 2 <= nthreads ? 2 : 1;
+    int S = 1;                                         // lane stride: every S-th lane takes a ray while the grid has room
+    while (S < smax && total * (S * 2) <= nthreads) S *= 2;
     const long long gtid = (long long)blockIdx.x * kRaysBlock + threadIdx.x;
     if (gtid % S) return;
     for (long long w = gtid / S; w < total; w += nthreads / S) {
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
     }
 }
 
@@ -314,27 +343,18 @@ k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint3
         if (lx >= gx || ly >= gy) continue;
         const int idx = lx + add_x, idy = ly + add_y;
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // cache copy (optional) + colorize, one streaming pass.  A warp takes 128 consecutive pixels per trip: the colour words as
 // one uint4 per lane, the positions as four fully coalesced float4 rows (lane l moves pixels l, 32+l, 64+l, 96+l), so every
-// load/store instruction covers 512 contiguous bytes.  Hole words inside the gap filter's bounds (kernel.cl:416) are listed
-// for k_fill_compute (one warp-aggregated atomic per warp that saw any).
-__device__ __forceinline__ bool gap_candidate(uint32_t v, int p, int res_x, int res_y)
-{
-    if (v != kHole) return false;
-    const int idy = p / res_x, idx = p - idy * res_x;
-    return !(idx >= res_x - 1 || idy >= res_y - 1 || idx <= 1 || idy <= 1);
-}
-
+// load/store instruction covers 512 contiguous bytes.
 __global__ void __launch_bounds__(256)
 k_copy_colorize(const uint32_t *__restrict__ src_s, const float4 *__restrict__ src_b, uint32_t *__restrict__ dst_s,
-                float4 *__restrict__ dst_b, uint32_t *__restrict__ tex, int res_x, int res_y, PatchList patch)
+                float4 *__restrict__ dst_b, uint32_t *__restrict__ tex, int n)
 {
-    const int n = res_x * res_y;
     const bool vec = (((uintptr_t)src_s | (uintptr_t)dst_s | (uintptr_t)tex) & 15u) == 0;
     const int lane = threadIdx.x & 31;
     const int nchunks = vec ? n >> 7 : 0;                              // whole 128-pixel chunks
@@ -348,63 +368,68 @@ k_copy_colorize(const uint32_t *__restrict__ src_s, const float4 *__restrict__ s
             dst_b[base + lane] = b0; dst_b[base + 32 + lane] = b1; dst_b[base + 64 + lane] = b2; dst_b[base + 96 + lane] = b3;
         }
         if (tex) reinterpret_cast<uint4 *>(tex + base)[lane] = make_uint4(colorize_word(v.x), colorize_word(v.y), colorize_word(v.z), colorize_word(v.w));
-        const bool any = v.x == kHole || v.y == kHole || v.z == kHole || v.w == kHole;
-        if (__any_sync(0xffffffffu, any)) {
-            const int p = base + 4 * lane;
-            unsigned int flags = 0;
-            if (any) flags = (gap_candidate(v.x, p, res_x, res_y) ? 1u : 0u) | (gap_candidate(v.y, p + 1, res_x, res_y) ? 2u : 0u) |
-                             (gap_candidate(v.z, p + 2, res_x, res_y) ? 4u : 0u) | (gap_candidate(v.w, p + 3, res_x, res_y) ? 8u : 0u);
-            const unsigned int cnt = (unsigned int)__popc(flags);
-            unsigned int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned int slot0 = 0;
-            if (lane == 0 && total) slot0 = atomicAdd(patch.count, total);
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0) + incl - cnt;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (flags & (1u << i)) patch.items[slot0++] = make_uint2((uint32_t)(p + i), kHole);
-        }
     }
     for (int p = (nchunks << 7) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const uint32_t v = src_s[p];
         if (dst_s) { dst_s[p] = v; dst_b[p] = src_b[p]; }
         if (tex) tex[p] = colorize_word(v);
-        if (gap_candidate(v, p, res_x, res_y)) patch.items[atomicAdd(patch.count, 1u)] = make_uint2((uint32_t)p, kHole);
     }
 }
 
-// Small-gap filter (raycast_fillhole2, kernel.cl:404-470) on the listed hole pixels, snapshot semantics: every pixel is
-// computed from the frame `src_s`, which nothing modifies until k_apply_patches (the reference filters in place; linear
-// offsets past the image read the words that follow it, as there).  The filtered word goes to the colorized image at once
-// and into the list for the in-place write.
-__global__ void __launch_bounds__(256)
-k_fill_compute(const uint32_t *__restrict__ src_s, uint32_t *__restrict__ tex, PatchList patch, int res_x)
+// Small-gap filter (raycast_fillhole2, kernel.cl:404-470) on the listed hole pixels, snapshot semantics.  `snap` holds the
+// pre-filter image of pixels [0, n) and is not modified while this runs (exact mode: the cache copy in buffer 2, which the
+// next frame only reads; ping-pong: the destination slot); linear offsets >= n (the 5x5 search near the last rows) read
+// `beyond`, the words that follow the image in the reference's layout.  The filtered word goes to the colorized image at
+// once and into value[i] for the in-place write (k_apply_patches).
+struct SnapView {
+    const uint32_t *snap, *beyond; int n;
+    __device__ __forceinline__ uint32_t operator[](int i) const { return i < n ? snap[i] : beyond[i]; }
+};
+__device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, int res_x)
 {
-    const unsigned int cnt = patch.count[0];
+    const uint32_t c1 = s[ofs + 1], c2 = s[ofs - 1], c3 = s[ofs + res_x], c4 = s[ofs - res_x];
+    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
+        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
+    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
+    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+    uint32_t col = c1;                                   // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
+    if (col == kHole) col = c3;                          // i = 2
+    if (col == kHole) col = s[ofs + 1 + res_x];          // i = 3
+    if (col == kHole)
+        for (int i = -2; i < 3 && col == kHole; ++i)
+            for (int j = -2; j < 3; ++j) {
+                if (col != kHole) break;
+                col = s[ofs + i + j * res_x];
+            }
+    return col;
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_list(SnapView view, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid, const unsigned int *__restrict__ resid_count,
+            PatchList patch, int res_x)
+{
+    const unsigned int cnt = resid_count[0];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const int p = (int)patch.items[i].x;
-        const uint32_t f = fillhole2_pixel(src_s, p, res_x);
-        patch.items[i].y = f;
-        if (f != kHole && tex) tex[p] = colorize_word(f);
+        const int p = (int)resid[i];
+        uint32_t f = kHole;
+        if (view[p] == kHole) {                          // else: listed before a ray filled it
+            f = fillhole2_view(view, p, res_x);
+            if (f != kHole && tex) tex[p] = colorize_word(f);
+        }
+        patch.value[i] = f;
     }
 }
 
-// the in-place half of the filter, after every read of the pass; the last CTA to have read the count re-arms the list.
-// out_s == nullptr (ping-pong mode: the image is the only consumer) just re-arms.
+// The in-place half of the filter (the reference writes the filtered words into the frame itself).  Nothing inside the
+// pipeline reads them -- the next frame's resolve pass rewrites every pixel of the frame -- so this runs only when the
+// host can observe buffer 0 before the next frame (flush_patches in svo_abi.cu).
 __global__ void __launch_bounds__(256)
-k_apply_patches(uint32_t *__restrict__ out_s, PatchList patch)
+k_apply_patches(uint32_t *__restrict__ out_s, const uint32_t *__restrict__ resid, const unsigned int *__restrict__ resid_count, PatchList patch)
 {
-    const unsigned int cnt = patch.count[0];
-    if (out_s)
-        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-            const uint2 e = patch.items[i];
-            if (e.y != kHole) out_s[e.x] = e.y;
-        }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&patch.count[1], 1u) == gridDim.x - 1) { patch.count[0] = 0; patch.count[1] = 0; __threadfence(); }
+    const unsigned int cnt = resid_count[0];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t f = patch.value[i];
+        if (f != kHole) out_s[resid[i]] = f;
     }
 }
 

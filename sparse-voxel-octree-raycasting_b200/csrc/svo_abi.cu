@@ -39,14 +39,24 @@ static svo_ctx_t need_ctx()
 }
 svo_ctx_t svo_need_ctx() { return need_ctx(); }
 
-// The fused frame writes its gap-filter results into buffer 0 on the second stream (k_apply_patches), off the critical
-// path.  Anything issued on the main stream that may touch buffer 0 is ordered behind that first.
-static void join_patches(svo_ctx_t c)
+// The fused frame computes its gap filter on the second stream (k_fill_compute: colorized image + patch list) and leaves
+// the filter's in-place write into buffer 0 pending: inside the pipeline nothing reads it (the next frame rewrites buffer
+// 0).  Whenever the host could observe buffer 0 -- a sync, a read-back, a launch through the kernel API -- the pending
+// write is issued first, so every observation sees what the reference sequence leaves.
+static void flush_patches(svo_ctx_t c)
 {
-    if (!c->patch_pending) return;
-    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_patch_done, 0));
-    c->patch_pending = false;
+    if (c->fill_outstanding) {                       // the colorized image / patch list of the last frame are still being written
+        CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0));
+        c->fill_outstanding = false;
+    }
+    if (!c->patch_target) return;
+    {
+        LaunchScope ls(c, "k_apply_patches");
+        svo::k_apply_patches<<<64, 256, 0, c->stream>>>(c->patch_target, c->patch_resid, c->patch_count, c->patch);
+    }
+    c->patch_target = nullptr;
 }
+static void join_patches(svo_ctx_t c) { flush_patches(c); }
 
 extern "C" int svo_device_count(void)
 {
@@ -77,7 +87,7 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
-    CU_CHECK(cudaEventCreateWithFlags(&c->ev_patch_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_fill_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     return c;
@@ -96,9 +106,8 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
-    cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_patch_done);
-    if (c->patch.items) cudaFree(c->patch.items);
-    if (c->patch.count) cudaFree(c->patch.count);
+    cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_fill_done);
+    if (c->patch.value) cudaFree(c->patch.value);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (auto &e : c->present_ready) if (e) cudaEventDestroy(e);
@@ -222,7 +231,7 @@ extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, in
     }
     CU_CHECK(cudaEventRecord(c->present_ready[slot], c->stream));
     CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->present_ready[slot], 0));
-    if (c->patch_event_valid) CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_patch_done, 0));   // the gap filter's pixels
+    if (c->fill_event_valid) CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_fill_done, 0));   // the gap filter's pixels
     CU_CHECK(cudaMemcpyAsync(host_dst, src->dptr, size, cudaMemcpyDeviceToHost, c->copy_stream));
     CU_CHECK(cudaEventRecord(c->present_done[slot], c->copy_stream));
 }
@@ -255,9 +264,12 @@ static void prof_flush(svo_ctx_t c)
     if (c->prof_pending.empty()) return;
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
+    c->timeline.clear();
     for (auto &r : c->prof_pending) {
-        float ms = 0.f;
+        float ms = 0.f, t0 = 0.f;
         CU_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+        CU_CHECK(cudaEventElapsedTime(&t0, c->prof_pending.front().a, r.a));
+        if (c->timeline.size() < 4096) c->timeline.push_back({r.name, t0, t0 + ms});
         auto &acc = c->prof_acc[r.name];
         acc.first += ms; acc.second += 1;
         c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
@@ -286,6 +298,22 @@ extern "C" int svo_profile_names(char *buf, size_t bufsize)
     for (auto &kv : c->prof_acc) { all += kv.first; all += "\n"; }
     snprintf(buf, bufsize, "%s", all.c_str());
     return (int)c->prof_acc.size();
+}
+
+// launches of the last flushed profiling batch as "name start_us end_us" lines (both streams, relative to the first launch)
+extern "C" int svo_profile_timeline(char *buf, size_t bufsize)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c || !buf || !bufsize) return -1;
+    prof_flush(c);
+    std::string all;
+    char line[160];
+    for (auto &t : c->timeline) {
+        snprintf(line, sizeof line, "%s %.2f %.2f\n", t.name, t.start_ms * 1000.0, t.end_ms * 1000.0);
+        all += line;
+    }
+    snprintf(buf, bufsize, "%s", all.c_str());
+    return (int)c->timeline.size();
 }
 
 extern "C" size_t svo_round_up(int group_size, int global_size)       // src/ocl.h:188-198
@@ -327,8 +355,8 @@ static void ensure_key(svo_ctx_t c, size_t pixels)
 static void ensure_fused_scratch(svo_ctx_t c, size_t ctas, size_t pixels)
 {
     if (!c->fs.counters) {
-        CU_CHECK(cudaMalloc(&c->fs.counters, 16));
-        CU_CHECK(cudaMemsetAsync(c->fs.counters, 0, 16, c->stream));
+        CU_CHECK(cudaMalloc(&c->fs.counters, 32));
+        CU_CHECK(cudaMemsetAsync(c->fs.counters, 0, 32, c->stream));
     }
     if (c->fs_ctas < ctas) {
         if (c->fs.scan_state) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaFree(c->fs.scan_state)); }
@@ -679,6 +707,7 @@ extern "C" void svo_end_all_kernels(void)                             // src/ocl
 {
     svo_ctx_t c = need_ctx();
     if (!c) return;
+    flush_patches(c);
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
 }
@@ -711,11 +740,10 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
 
     const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     ensure_key(c, n);
-    ensure_fused_scratch(c, ncta + 64, 1);
+    ensure_fused_scratch(c, ncta + 64, 2 * (size_t)n);                     // two residual-hole lists, alternating frames
     if (c->patch_pixels < n) {
-        if (c->patch.items) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaFree(c->patch.items)); }
-        CU_CHECK(cudaMalloc(&c->patch.items, (size_t)n * sizeof(uint2)));
-        if (!c->patch.count) { CU_CHECK(cudaMalloc(&c->patch.count, 8)); CU_CHECK(cudaMemsetAsync(c->patch.count, 0, 8, c->stream)); }
+        if (c->patch.value) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaFree(c->patch.value)); }
+        CU_CHECK(cudaMalloc(&c->patch.value, (size_t)n * 4));
         c->patch_pixels = n;
     }
     const bool strips = (res_x % 16) || (res_y % 16);
@@ -735,10 +763,12 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const Rect tile = {add_x, add_y, add_x + gx < res_x ? add_x + gx : res_x, add_y + gy < res_y ? add_y + gy : res_y};
     const bool overlap = !getenv("SVO_NO_OVERLAP");
     c->epoch = (c->epoch + 1) & 0x3fffffffu;
-    if (c->epoch == 0) c->epoch = 2;                                       // keeps the parity sequence alternating
+    if (c->epoch == 0) c->epoch = 4;                                       // keeps the mod-4 counter rotation in step
+    FusedScratch fs = c->fs;                                               // this frame's view of the scratch
+    fs.resid = c->fs.resid + (size_t)(c->epoch & 1u) * n;                  // the other list may still be read (second stream)
+    fs.resid_count = c->fs.counters + 4 + (c->epoch & 3u);                 // rotating: re-armed two frames ahead
+    unsigned int *next_resid_count = c->fs.counters + 4 + ((c->epoch + 2) & 3u);   // while the next frame fills another one
 
-    // ping-pong: the previous frame's gap filter still reads the slot this frame's scatter is about to invalidate pixels in
-    if (pingpong) join_patches(c);
     if (frame < 2) {                                                       // :150-154 (the destination is rewritten below)
         if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
         else do_memset(c, screen, n, kHole, n * 3);
@@ -746,60 +776,66 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     auto launch_tile = [&](cudaStream_t st) {                              // :361-387 tile refresh
         LAUNCH_ON(c, "k_rays_tile", st);
         const int grid = (((gx + 7) / 8) * ((gy + 3) / 4) * 32 + kRaysBlock - 1) / kRaysBlock;
-        if (c->depth == 11) k_rays_tile<11><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, c->fs);
-        else                k_rays_tile<14><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, c->fs);
+        if (c->depth == 11) k_rays_tile<11><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, fs);
+        else                k_rays_tile<14><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, fs);
     };
+    // A pending in-place gap-filter write of the previous frame is dead now: this frame rewrites all of buffer 0.
+    c->patch_target = nullptr;
+    // second stream: everything it does for this frame comes after what the main stream has done so far
+    CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
+    CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
     if (overlap) {
-        // the tile rays depend on nothing of this frame: start them first, on the second stream, once the previous
-        // frame (which read and wrote the destination slot) has finished
-        CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
-        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
+        // the tile rays depend on nothing of this frame: start them first, concurrently with the reprojection
         launch_tile(c->stream2);
         CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
     }
     {   // :177-198 source buffers in ascending offset = the reference's launch order
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = (unsigned int)src_count * n;
-        k_proj_scatter2<<<bw_grid(c, nsrc, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, nullptr, res_x, res_y,
-                                                                        (unsigned int)src_first * n, nsrc, pc);
+        k_proj_scatter2<<<(nsrc + 255) / 256, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, (unsigned int)src_first * n, nsrc, pc);
     }
-    join_patches(c);                                                       // the previous frame's filtered words are in buffer 0
+    // ping-pong: the previous frame's gap filter (second stream) reads the slot rendered into two frames ago... which is this
+    // frame's destination only every other frame; waiting here is always safe and long satisfied
+    if (pingpong && c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
     {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
         LAUNCH(c, "k_resolve_gather");
-        GatherArgs ga = {screen, back, c->key, idb, c->fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc};
+        GatherArgs ga = {screen, back, c->key, idb, fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc, next_resid_count};
         k_resolve_gather<<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
     }
     {   // :332-359 hole rays, count on the device
         LAUNCH(c, "k_rays_holes");
         const int grid = c->num_sms * 32;
-        if (c->depth == 11) k_rays_holes<11><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, c->fs);
-        else                k_rays_holes<14><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, c->fs);
+        static const int smax = getenv("SVO_HOLES_SMAX") ? atoi(getenv("SVO_HOLES_SMAX")) : 8;
+        if (c->depth == 11) k_rays_holes<11><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
+        else                k_rays_holes<14><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
     }
     if (overlap) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
     else launch_tile(c->stream);
     uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
     if (!pingpong || tex) {
+        // exact mode: the previous frame's gap filter (second stream) reads the cache copy this pass overwrites
+        if (!pingpong && c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
         {   // :394-405 cache copy (target 2) + :429-437 colorize, one streaming pass
             LAUNCH(c, "k_copy_colorize");
             k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
                 dscreen, reinterpret_cast<const float4 *>(dback), pingpong ? nullptr : screen + 2 * (size_t)n,
-                pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, res_x, res_y, c->patch);
+                pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
         }
-        // :411-422 gap filter on the listed hole pixels: second stream, nobody on the main stream waits for it before the
-        // next frame's resolve pass (join_patches)
+        // :411-422 gap filter, second stream: reads the pre-filter image (exact: the cache copy just made, which the next
+        // frame only reads; ping-pong: the destination slot), writes the colorized image and the patch list
         CU_CHECK(cudaEventRecord(c->ev_copy_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_copy_done, 0));
         {
-            LAUNCH_ON(c, "k_fill_compute", c->stream2);
-            k_fill_compute<<<c->num_sms * 2, 256, 0, c->stream2>>>(dscreen, tex, c->patch, res_x);
+            LAUNCH_ON(c, "k_fill_list", c->stream2);
+            const SnapView view = {pingpong ? dscreen : screen + 2 * (size_t)n, dscreen, (int)n};
+            k_fill_list<<<c->num_sms * 2, 256, 0, c->stream2>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
         }
-        {
-            LAUNCH_ON(c, "k_apply_patches", c->stream2);
-            k_apply_patches<<<64, 256, 0, c->stream2>>>(pingpong ? nullptr : dscreen, c->patch);
-        }
-        CU_CHECK(cudaEventRecord(c->ev_patch_done, c->stream2));
-        c->patch_pending = true;
-        c->patch_event_valid = true;
+        CU_CHECK(cudaEventRecord(c->ev_fill_done, c->stream2));
+        c->fill_event_valid = true;
+        c->fill_outstanding = true;
+        c->patch_target = pingpong ? nullptr : dscreen;   // exact mode: buffer 0 still lacks the filtered words
+        c->patch_count = fs.resid_count;
+        c->patch_resid = fs.resid;
     }
     c->last_slot = dst_slot;
     c->have_frame = true;

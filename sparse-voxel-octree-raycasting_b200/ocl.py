@@ -77,6 +77,7 @@ _svo_profile_enable = _sig("svo_profile_enable", None, _i)
 _svo_profile_reset = _sig("svo_profile_reset", None)
 _svo_profile_get = _sig("svo_profile_get", _i, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64))
 _svo_profile_names = _sig("svo_profile_names", _i, C.c_char_p, _sz)
+_svo_profile_timeline = _sig("svo_profile_timeline", _i, C.c_char_p, _sz)
 _svo_host_alloc = _sig("svo_host_alloc", _vp, _sz)
 _svo_host_free = _sig("svo_host_free", None, _vp)
 _svo_copy_to_host_async = _sig("svo_copy_to_host_async", None, _vp, _vp, _sz, _sz)
@@ -280,6 +281,17 @@ def profile_all():
         ms, cnt = C.c_double(), C.c_uint64()
         _svo_profile_get(name.encode(), C.byref(ms), C.byref(cnt))
         out[name] = (ms.value, cnt.value)
+    return out
+
+
+def profile_timeline():
+    """[(cuda kernel name, start_us, end_us)] of the launches since the last flush, all streams, relative to the first."""
+    buf = C.create_string_buffer(1 << 18)
+    _svo_profile_timeline(buf, 1 << 18)
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, a, b = line.split()
+        out.append((name, float(a), float(b)))
     return out
 
 
