@@ -56,6 +56,12 @@ def make_scene(svo, path):
     vox.free()
 
 
+def workload_name(scene_name):
+    """config.workload of both arms (b200 and --impl reference): BASELINE.json config 2."""
+    return (f"256-frame scripted flythrough, {RES_X}x{RES_Y}, full warping pipeline (reproject 2 buffers, 2x2 hole gather, hole raycast, "
+            f"8x4 tile refresh, cache copy, gap filter, colorize), scene: {scene_name}")
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -284,7 +290,7 @@ def main():
         line = {"impl": "reference", "metric": "warped_pipeline_fps_1920x1024", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": r["frames_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-                "config": {"workload": f"256-frame scripted flythrough, {RES_X}x{RES_Y}, full warping pipeline, scene: {scene_name}"},
+                "config": {"workload": workload_name(scene_name)},
                 "full_raycast_mrays_per_s": r["full_raycast_mrays_per_s"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -434,8 +440,7 @@ def main():
         line = {"metric": "warped_pipeline_fps_1920x1024", "value": fps, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-                "config": {"workload": f"256-frame scripted flythrough, {RES_X}x{RES_Y}, full warping pipeline (reproject 2 buffers, 2x2 hole gather, "
-                                       f"hole raycast, 8x4 tile refresh, cache copy, gap filter, colorize), scene: {scene_name}",
+                "config": {"workload": workload_name(scene_name),
                            "octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
                            "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} (one camera path per GPU, no communication)",
                            "l2_note": "working set per frame (2 x 20 B/pixel x 1.97 Mpixel + octree) exceeds nothing by construction: inputs change every frame; "

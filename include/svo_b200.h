@@ -59,9 +59,10 @@ void     *svo_mem_device_ptr(svo_mem_t mem);                             /* raw 
 size_t    svo_mem_size(svo_mem_t mem);
 
 /* ---- kernel launch (positional by-value arguments, exactly as the call sites in src/raycast.h) -- */
-/* names: memset memcpy raycast_proj raycast_counthole raycast_sumids raycast_writeids raycast_holes
- *        raycast_fine_2 raycast_fillhole2 raycast_colorize; raycast_fillhole and raycast_fine resolve
- *        but are the kernels the reference disables with if(0) (src/raycast.h:205,234): launching them is an error. */
+/* names: all 12 __kernel entry points of kernel/kernel.cl -- memset memcpy raycast_proj raycast_counthole raycast_sumids
+ *        raycast_writeids raycast_holes raycast_fine_2 raycast_fillhole2 raycast_colorize, and raycast_fillhole /
+ *        raycast_fine, which the reference keeps behind if(0) at their call sites (src/raycast.h:205,234); their
+ *        argument lists are the ones written there (:210-217, :239-257). */
 svo_kernel_t svo_get_kernel(const char *name);                           /* ocl_get_kernel() src/ocl.h:148-153 */
 void svo_begin(svo_kernel_t *kernel, int globalx, int globaly, int localx, int localy); /* ocl_begin() src/ocl.h:229-237 */
 void svo_param(size_t size, const void *ptr);                            /* ocl_param() src/ocl.h:238-241 */

@@ -80,6 +80,10 @@ class CpuOracle:
                          f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f, f)
         self._fine2 = fn("raycast_fine_2", None, i, i, i, i, i, u32p, f32p, u32p, u, i, i, i, i, i,
                          f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f, f)
+        self._fine = fn("raycast_fine", None, i, i, i, i, u32p, f32p, u32p, u, i, i, i, i, i,
+                        f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f, f)
+        i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+        self._fillhole = fn("raycast_fillhole", None, i, i, i, i, i, u32p, f32p, i32p, i32p, vp, i, i, i)
         self._fillhole2 = fn("raycast_fillhole2", None, i, i, i, i, u32p, vp, i, i, i)
         self._colorize = fn("raycast_colorize", None, i, i, i, i, i, u32p, u32p, i, i)
         self._max_threads = fn("max_threads", i)
@@ -145,6 +149,19 @@ class CpuOracle:
         gy = res_y // 4 if gy is None else gy
         self._fine2(gx, gy, 16, 16, threads, screen, back, octree, root, res_x, res_y, frame, add_x, add_y,
                     z, z, z, z, _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz), fovx, fovy)
+
+    def raycast_fine(self, screen, back, octree, root, res_x, res_y, frame, add_x, add_y, m0, mx, my, mz,
+                     fovx=1.0, fovy=1.0, gx=None, gy=None):
+        """kernel.cl:696-843 with the launch geometry of its (disabled) call site, src/raycast.h:238."""
+        z = _vec4([0])
+        gx = res_x // 4 if gx is None else gx
+        gy = res_y // 4 if gy is None else gy
+        self._fine(gx, gy, 16, 16, screen, back, octree, root, res_x, res_y, frame, add_x, add_y,
+                   z, z, z, z, _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz), fovx, fovy)
+
+    def raycast_fillhole(self, screen, back, xbuf, ybuf, res_x, res_y, frame=0, threads=1):
+        """kernel.cl:342-401 with the launch geometry of its (disabled) call site, src/raycast.h:209."""
+        self._fillhole(res_x, res_y, 16, 16, threads, screen, back, xbuf, ybuf, None, res_x, res_y, frame)
 
     def raycast_fillhole2(self, screen, res_x, res_y, frame=0):
         self._fillhole2(res_x, res_y, 16, 16, screen, None, res_x, res_y, frame)

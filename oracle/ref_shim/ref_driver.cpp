@@ -213,6 +213,28 @@ void ref_raycast_colorize(int gx, int gy, int lx, int ly, int threads, uint *scr
     ndrange(gx, gy, lx, ly, threads, [&] { raycast_colorize(screen, tex, w, h); });
 }
 
+// src/raycast.h:205-219 (disabled there with if(0)); race free: reads depth words, writes only its own colour word.
+// The kernel reads a_xbuffer/a_ybuffer at an offset built from xi/yj, which it leaves uninitialised when no neighbour
+// is nearer (kernel.cl:372-384; the value read is then unused): the library is built with -ftrivial-auto-var-init=zero.
+void ref_raycast_fillhole(int gx, int gy, int lx, int ly, int threads, uint *screen, float *back, int *xbuf, int *ybuf,
+                          float *zbuf, int res_x, int res_y, int frame)
+{
+    ndrange(gx, gy, lx, ly, threads, [&] { raycast_fillhole(screen, back, xbuf, ybuf, zbuf, res_x, res_y, frame); });
+}
+
+// src/raycast.h:234-260 (disabled there with if(0)); serial like raycast_proj (work items of neighbouring 2x2 cells can
+// touch each other's pixels when add_x / res_x are odd)
+void ref_raycast_fine(int gx, int gy, int lx, int ly, uint *screen, float *back, uint *octree,
+                      uint root, int res_x, int res_y, int frame, int add_x, int add_y,
+                      const float *cam, const float *origin, const float *dx, const float *dy,
+                      const float *m0, const float *mx, const float *my, const float *mz, float fovx, float fovy)
+{
+    ndrange(gx, gy, lx, ly, 1, [&] {
+        raycast_fine(screen, back, octree, root, res_x, res_y, frame, add_x, add_y,
+                     f4(cam), f4(origin), f4(dx), f4(dy), f4(m0), f4(mx), f4(my), f4(mz), fovx, fovy);
+    });
+}
+
 int ref_max_threads() { return omp_get_max_threads(); }
 
 } // extern "C"

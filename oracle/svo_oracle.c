@@ -610,6 +610,60 @@ void orc_raycast_fine_2(int gx, int gy, int lx, int ly, int threads, uint32_t *s
     NDRANGE_END
 }
 
+/* kernel/kernel.cl:696-843 raycast_fine (disabled at its call site, src/raycast.h:234): one ray per 2x2 cell of the
+ * rectangle starting at (add_x, add_y) -- the first hole pixel of the cell in the order (0,0),(1,0),(0,1),(1,1), else the
+ * pixel ((frame>>2)&1, (frame>>3)&1) (:723-742); the stores after the `return` at :806 are dead.  Serial: with odd
+ * add_x / res_x neighbouring cells share pixels through the linear offsets. */
+void orc_raycast_fine(int gx, int gy, int lx, int ly, uint32_t *screen, float *back,
+                      const uint32_t *octree, uint32_t root, int res_x, int res_y, int frame, int add_x, int add_y,
+                      const float *cam, const float *origin, const float *dx, const float *dy,
+                      const float *m0, const float *mx, const float *my, const float *mz, float fovx, float fovy)
+{
+    (void)cam; (void)origin; (void)dx; (void)dy;
+    NDRANGE_BEGIN(gx, gy, lx, ly, 1)
+        int idx = gid0 * 2 + add_x, idy = gid1 * 2 + add_y;
+        if (idx >= res_x || idy >= res_y) continue;
+        uint32_t col = 0;
+        for (int i = 0; i < 4; ++i) {
+            col = screen[(idy + (i >> 1)) * res_x + idx + (i & 1)];
+            if (col == HOLE) { idx += i & 1; idy += i >> 1; break; }
+        }
+        if (col != HOLE) { idx += (frame >> 2) & 1; idy += (frame >> 3) & 1; }
+        shade_pixel(screen, back, octree, root, res_x, res_y, idx, idy, m0, mx, my, mz, fovx, fovy);
+    NDRANGE_END
+}
+
+/* kernel/kernel.cl:342-401 raycast_fillhole (disabled at its call site, src/raycast.h:205): punches a hole where the depth
+ * (w of the coordinate buffer) jumps against the nearer of the up/left neighbours AND the per-pixel motion vectors differ.
+ * loopi(-1,1) x loopj(-1,1) visits i, j in {-1, 0} (src/core.h loop macros); xi / yj stay uninitialised in the reference
+ * when no neighbour is nearer -- the words read through them are then unused (:385 returns) -- zero here.
+ * `min(z0,z1)*Z_CONTINUITY*4.0` is evaluated in double (Z_CONTINUITY = 0.00625*1.0, :20). */
+void orc_raycast_fillhole(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, const float *back,
+                          const int *xbuf, const int *ybuf, const float *zbuf, int res_x, int res_y, int frame)
+{
+    (void)zbuf; (void)frame;
+    NDRANGE_BEGIN(gx, gy, lx, ly, threads)
+        const int idx = gid0, idy = gid1;
+        if (idx >= res_x - 4 || idy >= res_y - 4 || idx < 3 || idy < 3) continue;
+        const uint32_t of = (uint32_t)(idy * res_x + idx);
+        if (screen[of] == HOLE) continue;
+        const float z0 = back[of * 4 + 3];
+        float z1 = z0;
+        int xi = 0, yj = 0;
+        for (int i = -1; i < 1; ++i)
+            for (int j = -1; j < 1; ++j) {
+                const float z = back[(of + j * res_x + i) * 4 + 3];
+                if (z < z1) { xi = i; yj = j; z1 = z; }
+            }
+        const int dx0 = xbuf[of], dy0 = ybuf[of];
+        const int oij = (int)of + yj * res_x + xi;
+        const int dx = xbuf[oij], dy = ybuf[oij];
+        if (z0 <= z1) continue;
+        if (fabs((double)(z1 - z0)) > (double)(z0 < z1 ? z0 : z1) * (0.00625 * 1.0) * 4.0)
+            if (abs(dx - dx0) > 0 || abs(dy - dy0) > 0) screen[of] = HOLE;
+    NDRANGE_END
+}
+
 /* kernel/kernel.cl:404-470 as a pure function of the pre-pass image `s` (snapshot semantics).
  * Offsets are linear, exactly as in the reference: the 5x5 search may wrap across rows and read
  * up to res_x+... words past buffer 0 (i.e. into buffer 1). */

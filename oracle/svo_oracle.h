@@ -51,6 +51,13 @@ void orc_raycast_holes(int gx, int gy, int lx, int ly, int threads, uint32_t *sc
                        int res_x, int res_y, int frame, int idbuf_size,
                        const float *cam, const float *origin, const float *dx, const float *dy,
                        const float *m0, const float *mx, const float *my, const float *mz, float fovx, float fovy);
+/* the two kernels the reference disables at their call sites (src/raycast.h:205,234) */
+void orc_raycast_fine(int gx, int gy, int lx, int ly, uint32_t *screen, float *back,
+                      const uint32_t *octree, uint32_t root, int res_x, int res_y, int frame, int add_x, int add_y,
+                      const float *cam, const float *origin, const float *dx, const float *dy,
+                      const float *m0, const float *mx, const float *my, const float *mz, float fovx, float fovy);
+void orc_raycast_fillhole(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, const float *back,
+                          const int *xbuf, const int *ybuf, const float *zbuf, int res_x, int res_y, int frame);
 void orc_raycast_fine_2(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back,
                         const uint32_t *octree, uint32_t root, int res_x, int res_y, int frame, int add_x, int add_y,
                         const float *cam, const float *origin, const float *dx, const float *dy,

@@ -542,7 +542,7 @@ extern "C" void svo_memset(svo_mem_t dst, uint32_t dstofs, uint32_t val, uint32_
 // ------------------------------------------------------------------------------------------------
 enum KernelId {
     K_MEMSET, K_MEMCPY, K_PROJ, K_COUNTHOLE, K_SUMIDS, K_WRITEIDS, K_HOLES, K_FINE_2, K_FILLHOLE2, K_COLORIZE,
-    K_FILLHOLE_DISABLED, K_FINE_DISABLED, K_COUNT
+    K_FILLHOLE, K_FINE, K_COUNT
 };
 enum ArgKind : unsigned char { A_MEM, A_I32, A_F4, A_F1, A_F4_DEAD };   // A_F4_DEAD: float4 the kernels never read (not copied)
 
@@ -566,8 +566,9 @@ static svo_kernel_s g_kernels[K_COUNT] = {
                                       A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4, A_F4, A_F4, A_F4, A_F1, A_F1}},     // src/raycast.h:367-385
     {K_FILLHOLE2, "raycast_fillhole2", 5, {A_MEM, A_MEM, A_I32, A_I32, A_I32}},                      // src/raycast.h:416-420
     {K_COLORIZE, "raycast_colorize", 4, {A_MEM, A_MEM, A_I32, A_I32}},                               // src/raycast.h:432-435
-    {K_FILLHOLE_DISABLED, "raycast_fillhole", 0, {}},                                                // disabled: src/raycast.h:205
-    {K_FINE_DISABLED, "raycast_fine", 0, {}},                                                        // disabled: src/raycast.h:234
+    {K_FILLHOLE, "raycast_fillhole", 8, {A_MEM, A_MEM, A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32}},  // src/raycast.h:210-217 (if(0) there)
+    {K_FINE, "raycast_fine", 19, {A_MEM, A_MEM, A_MEM, A_I32, A_I32, A_I32, A_I32, A_I32, A_I32,
+                                  A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4_DEAD, A_F4, A_F4, A_F4, A_F4, A_F1, A_F1}},         // src/raycast.h:239-257 (if(0) there)
 };
 
 extern "C" svo_kernel_t svo_get_kernel(const char *name)
@@ -618,10 +619,6 @@ extern "C" void svo_end(void)
     svo_ctx_t c = need_ctx();
     svo_kernel_t k = g_current;
     if (!c || !k) return;
-    if (k->id == K_FILLHOLE_DISABLED || k->id == K_FINE_DISABLED) {
-        svo_fail(-59, "CL_INVALID_OPERATION: kernel '%s' is disabled in the reference (if(0)) and not provided", k->name);
-        return;
-    }
     if (g_narg != k->nargs) { svo_fail(-52, "CL_INVALID_KERNEL_ARGS: '%s' takes %d arguments, %d given", k->name, k->nargs, g_narg); return; }
     for (int i = 0; i < k->nargs; ++i) {
         static const size_t want[] = {sizeof(void *), 4, 16, 4, 16};
@@ -683,6 +680,31 @@ extern "C" void svo_end(void)
         const int res_x = arg<int>(4), res_y = arg<int>(5), add_x = arg<int>(7), add_y = arg<int>(8);
         const RayCam cam = make_ray_cam(arg_f4(13), arg_f4(14), arg_f4(15), arg_f4(16), arg<float>(17), arg<float>(18));
         do_fine_2(c, screen, back, oct, arg<uint32_t>(3), res_x, res_y, gx, gy, add_x, add_y, cam);
+        break;
+    }
+    case K_FILLHOLE: {
+        uint32_t *screen = arg_u32p(0); float *back = arg_f32p(1);
+        const int *xb = (const int *)arg_u32p(2), *yb = (const int *)arg_u32p(3);
+        if (!screen || !back || !xb || !yb) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_fillhole"); return; }
+        const int res_x = arg<int>(5), res_y = arg<int>(6);
+        if (gx > 0 && gy > 0) {
+            LAUNCH(c, "k_fillhole");
+            k_fillhole<<<dim3((gx + 31) / 32, (gy + 7) / 8), dim3(32, 8), 0, c->stream>>>(screen, back, xb, yb, res_x, res_y);
+        }
+        break;
+    }
+    case K_FINE: {
+        uint32_t *screen = arg_u32p(0); float *back = arg_f32p(1);
+        const uint32_t *oct = arg_u32p(2);
+        if (!screen || !back || !oct) { svo_fail(-38, "CL_INVALID_MEM_OBJECT: raycast_fine"); return; }
+        const int res_x = arg<int>(4), res_y = arg<int>(5), frame = arg<int>(6), add_x = arg<int>(7), add_y = arg<int>(8);
+        const RayCam cam = make_ray_cam(arg_f4(13), arg_f4(14), arg_f4(15), arg_f4(16), arg<float>(17), arg<float>(18));
+        if (gx > 0 && gy > 0) {
+            dim3 grid((gx + 31) / 32, (gy + 7) / 8);
+            LAUNCH(c, "k_raycast_fine");
+            if (c->depth == 11) k_raycast_fine<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, arg<uint32_t>(3), res_x, res_y, gx, gy, frame, add_x, add_y, cam);
+            else                k_raycast_fine<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, arg<uint32_t>(3), res_x, res_y, gx, gy, frame, add_x, add_y, cam);
+        }
         break;
     }
     case K_FILLHOLE2: {

@@ -332,4 +332,60 @@ k_raycast_fine_2(uint32_t *__restrict__ screen, float *__restrict__ back, const 
     trace_pixel<D>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two kernels the reference disables at their call sites (if(0), src/raycast.h:205,234).  They resolve by name and
+// launch like the others, so a host that re-enables the quality passes finds them.
+// ---------------------------------------------------------------------------------------------
+// raycast_fillhole (kernel/kernel.cl:342-401): punches a hole where the depth (w of the coordinate buffer) jumps against
+// the nearer of the up / left neighbours and the per-pixel motion vectors differ.  loopi(-1,1) x loopj(-1,1) visits
+// i, j in {-1, 0}; xi / yj are uninitialised in the reference when no neighbour is nearer (the words read through them
+// are then unused, :385 returns first): zero here.  The threshold `min(z0,z1)*Z_CONTINUITY*4.0` is a double product.
+__global__ void k_fillhole(uint32_t *__restrict__ screen, const float *__restrict__ back, const int *__restrict__ xbuf,
+                           const int *__restrict__ ybuf, int res_x, int res_y)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x, idy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (idx >= res_x - 4 || idy >= res_y - 4 || idx < 3 || idy < 3) return;
+    const uint32_t of = (uint32_t)(idy * res_x + idx);
+    if (screen[of] == kHole) return;
+    const float z0 = back[(size_t)of * 4 + 3];
+    float z1 = z0;
+    int xi = 0, yj = 0;
+#pragma unroll
+    for (int i = -1; i < 1; ++i)
+#pragma unroll
+        for (int j = -1; j < 1; ++j) {
+            const float z = back[(size_t)(of + j * res_x + i) * 4 + 3];
+            if (z < z1) { xi = i; yj = j; z1 = z; }
+        }
+    if (z0 <= z1) return;
+    const int oij = (int)of + yj * res_x + xi;
+    const int dx0 = xbuf[of], dy0 = ybuf[of], dx = xbuf[oij], dy = ybuf[oij];
+    if (fabs((double)(z1 - z0)) > (double)fminf(z0, z1) * (0.00625 * 1.0) * 4.0)
+        if (abs(dx - dx0) > 0 || abs(dy - dy0) > 0) screen[of] = kHole;
+}
+
+// raycast_fine (kernel/kernel.cl:696-843): one ray per 2x2 cell of the rectangle at (add_x, add_y) -- the first hole pixel
+// of the cell in the order (0,0),(1,0),(0,1),(1,1), else the pixel ((frame>>2)&1, (frame>>3)&1) (:723-742).  Everything
+// after the `return` at :806 is dead.  A warp covers 8x4 cells.
+template <int D>
+__global__ void __launch_bounds__(kRayBlock)
+k_raycast_fine(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
+               int res_x, int res_y, int gx, int gy, int frame, int add_x, int add_y, RayCam cam)
+{
+    __shared__ uint32_t stack[(D + 1) * kRayBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gx0 = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7), gy0 = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (gx0 >= gx || gy0 >= gy) return;
+    int idx = gx0 * 2 + add_x, idy = gy0 * 2 + add_y;
+    if (idx >= res_x || idy >= res_y) return;
+    uint32_t col = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        col = screen[(idy + (i >> 1)) * res_x + idx + (i & 1)];
+        if (col == kHole) { idx += i & 1; idy += i >> 1; break; }
+    }
+    if (col != kHole) { idx += (frame >> 2) & 1; idy += (frame >> 3) & 1; }
+    trace_pixel<D>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x);
+}
+
 }  // namespace svo

@@ -289,7 +289,7 @@ def test_golden_frames(svo):
 def test_errors_are_reported(svo):
     with pytest.raises(RuntimeError):
         svo.ocl_get_kernel("no_such_kernel")
-    k = svo.ocl_get_kernel("raycast_fine")          # disabled in the reference: resolves, cannot be launched
+    k = svo.ocl_get_kernel("raycast_fine")          # launched without its 19 arguments
     svo.ocl_begin(k, 16, 16, 16, 16)
     with pytest.raises(RuntimeError):
         svo.ocl_end()
@@ -394,3 +394,53 @@ def test_raycast_edge_scenes(svo, orc, scene):
             mi.free()
         ms.free(); mb.free()
     mo.free()
+
+
+@pytest.mark.parametrize("res", [(80, 48), (200, 120), (1920, 1024)])
+def test_disabled_kernel_fillhole(svo, orc, res):
+    """raycast_fillhole (kernel.cl:342-401; if(0) at its call site, src/raycast.h:205) through the kernel API with the
+    argument list of that call site: depth-discontinuity hole punch, bit-exact."""
+    rx, ry = res
+    n = rx * ry
+    rng = np.random.RandomState(rx)
+    screen = random_screen(rng, 4 * n, 0.2)
+    back = rng.rand(16 * n).astype(np.float32)
+    back[3:4 * n:4] = np.where(rng.rand(n) < 0.5, 10.0, 10.0 + 30.0 * rng.rand(n)).astype(np.float32)
+    xb = (rng.randint(0, 3, size=n) - 1).astype(np.int32)
+    yb = rng.randint(0, 2, size=n).astype(np.int32)
+    exp = screen.copy()
+    orc.raycast_fillhole(exp, back, xb, yb, rx, ry, threads=4)
+    ms, mb = svo.ocl_malloc(screen.nbytes, screen), svo.ocl_malloc(back.nbytes, back)
+    mx, my, mz = svo.ocl_malloc(xb.nbytes, xb), svo.ocl_malloc(yb.nbytes, yb), svo.ocl_malloc(4 * n)
+    launch(svo, "raycast_fillhole", rx, ry, 16, 16, [ms, mb, mx, my, mz, i32(rx), i32(ry), i32(4)])
+    got = ms.to_numpy()
+    assert (exp != screen).sum() > 0
+    assert np.array_equal(got, exp)
+    for m in (ms, mb, mx, my, mz):
+        m.free()
+
+
+@pytest.mark.parametrize("frame", [0, 1, 2, 3, 4, 8, 12])
+def test_disabled_kernel_fine(svo, orc, world, frame):
+    """raycast_fine (kernel.cl:696-843; if(0) at its call site, src/raycast.h:234) with that call site's launch geometry
+    and argument list: a quarter of the screen, one ray per 2x2 cell, holes first."""
+    octree, root = world
+    rx, ry = 320, 192
+    n = rx * ry
+    cam = ofr.camera_args((10, 22, 9), (0.4, 0.7, 0.0))
+    rng = np.random.RandomState(frame)
+    screen = rng.randint(0, 2 ** 24, size=4 * n).astype(np.uint32)
+    screen[rng.rand(4 * n) < 0.4] = HOLE
+    back = np.zeros(16 * n, dtype=np.float32)
+    add_x, add_y = (rx // 2) * (frame & 1), (ry // 2) * ((frame >> 1) & 1)              # src/raycast.h:236-237
+    exp_s, exp_b = screen.copy(), back.copy()
+    orc.raycast_fine(exp_s, exp_b, octree, root, rx, ry, frame, add_x, add_y, cam["v0"], *cam["cols"])
+    mo, ms, mb = svo.ocl_malloc(octree.nbytes, octree), svo.ocl_malloc(screen.nbytes, screen), svo.ocl_malloc(back.nbytes, back)
+    dead = (0, 0, 0, 0)
+    launch(svo, "raycast_fine", rx // 4, ry // 4, 16, 16,
+           [ms, mb, mo, C.c_uint32(root), i32(rx), i32(ry), i32(frame), i32(add_x), i32(add_y), dead, dead, dead, dead,
+            cam["v0"], *cam["cols"], C.c_float(1.0), C.c_float(1.0)])
+    assert np.array_equal(ms.to_numpy(), exp_s)
+    assert np.array_equal(mb.to_numpy(np.uint32), exp_b.view(np.uint32))
+    for m in (mo, ms, mb):
+        m.free()

@@ -104,3 +104,52 @@ def test_rle4_roundtrip(orc, ref, tmp_path):
     b, rb = orc.build_octree_rle4(path)
     assert ra == rb and np.array_equal(a, b)
     assert ref.num_voxels() == orc.num_voxels() == vox
+
+
+def _depth_image(rng, rx, ry, hole_frac):
+    """A screen / coordinate buffer pair with depth discontinuities and per-pixel motion vectors (raycast_fillhole input)."""
+    n = rx * ry
+    screen = rng.randint(0, 2 ** 32 - 1, size=4 * n, dtype=np.uint64).astype(np.uint32)
+    screen[rng.rand(4 * n) < hole_frac] = 0xFFFFFF00
+    back = rng.rand(16 * n).astype(np.float32)
+    z = np.where(rng.rand(n) < 0.5, 10.0, 10.0 + 30.0 * rng.rand(n)).astype(np.float32)      # flat areas with steps
+    back[3:4 * n:4] = z
+    xb = (rng.randint(0, 3, size=n) - 1).astype(np.int32)
+    yb = (rng.randint(0, 2, size=n)).astype(np.int32)
+    return screen, back, xb, yb
+
+
+def test_disabled_kernel_fillhole_matches_reference(orc, ref):
+    """raycast_fillhole (kernel.cl:342-401, if(0) at src/raycast.h:205): the restatement against the reference source."""
+    rng = np.random.RandomState(17)
+    for rx, ry in ((80, 48), (200, 120)):
+        for hole_frac in (0.0, 0.3):
+            screen, back, xb, yb = _depth_image(rng, rx, ry, hole_frac)
+            a, b = screen.copy(), screen.copy()
+            ref.raycast_fillhole(a, back, xb, yb, rx, ry)
+            orc.raycast_fillhole(b, back, xb, yb, rx, ry, threads=4)
+            assert np.array_equal(a, b)
+            punched = (a != screen).sum()
+            assert punched > 0 and np.array_equal(a[rx * ry:], screen[rx * ry:])
+
+
+@pytest.mark.parametrize("frame", [0, 1, 2, 3, 4, 8, 12])
+def test_disabled_kernel_fine_matches_reference(orc, ref, frame):
+    """raycast_fine (kernel.cl:696-843, if(0) at src/raycast.h:234) with the geometry of its call site: a quarter of the
+    screen, one ray per 2x2 cell, holes first, else the pixel picked by frame bits 2 and 3."""
+    octree, root = ref.build_octree(*scenes.small_world())
+    rx, ry = 160, 96
+    n = rx * ry
+    cam = fr.camera_args((10, 22, 9), (0.4, 0.7, 0.0))
+    rng = np.random.RandomState(frame)
+    screen = rng.randint(0, 2 ** 24, size=4 * n).astype(np.uint32)
+    screen[rng.rand(4 * n) < 0.4] = 0xFFFFFF00
+    back = np.zeros(16 * n, dtype=np.float32)
+    add_x, add_y = (rx // 2) * (frame & 1), (ry // 2) * ((frame >> 1) & 1)              # src/raycast.h:236-237
+    a_s, a_b, b_s, b_b = screen.copy(), back.copy(), screen.copy(), back.copy()
+    ref.raycast_fine(a_s, a_b, octree, root, rx, ry, frame, add_x, add_y, cam["v0"], *cam["cols"])
+    orc.raycast_fine(b_s, b_b, octree, root, rx, ry, frame, add_x, add_y, cam["v0"], *cam["cols"])
+    assert np.array_equal(a_s, b_s) and np.array_equal(a_b.view(np.uint32), b_b.view(np.uint32))
+    changed = (a_s != screen).reshape(4, ry, rx)[0]
+    assert changed.sum() > 0.8 * (rx // 4) * (ry // 4)
+    assert not changed[:, :add_x].any() and not changed[:add_y, :].any()
