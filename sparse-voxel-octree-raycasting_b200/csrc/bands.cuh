@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
                   const uint32_t *__restrict__ idb, int idsize, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs)
 {
-    __shared__ uint32_t stack[(D + 1) * kRaysBlock];
+    __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     const long long total = (long long)idb[0];
     const long long nthreads = (long long)gridDim.x * kRaysBlock;
     const int S = total * 4 <= nthreads ? 4 : total * 2 <= nthreads ? 2 : 1;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
                  BandMap m, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs)
 {
-    __shared__ uint32_t stack[(D + 1) * kRaysBlock];
+    __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     // owned rows of the rectangle, enumerated through the local row index so that every launched thread has work
     const int tiles_x = (gx + 7) / 8;
     const int lrows = m.local_rows;

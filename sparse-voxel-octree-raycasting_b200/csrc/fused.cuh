@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kRaysBlock)
 k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
              const uint32_t *__restrict__ idb, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs, int smax)
 {
-    __shared__ uint32_t stack[(D + 1) * kRaysBlock];
+    __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     const int idsize = (res_x / 16) * (res_y / 16);
     const long long total = (long long)idb[0];
     const long long nthreads = (long long)gridDim.x * kRaysBlock;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kRaysBlock)
 k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
             int res_x, int res_y, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs)
 {
-    __shared__ uint32_t stack[(D + 1) * kRaysBlock];
+    __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     const int tiles_x = (gx + 7) / 8, tiles_y = (gy + 3) / 4;
     const int total = tiles_x * tiles_y * 32;
     for (int t = blockIdx.x * kRaysBlock + threadIdx.x; t < total; t += gridDim.x * kRaysBlock) {

@@ -30,17 +30,24 @@ struct RayCam {                               // arguments shared by raycast_hol
 };
 
 __device__ __forceinline__ uint32_t ldg(const uint32_t *p) { return __ldg(p); }
+// ancestor stack: 32-bit shared-window addresses kept in a register (a generic pointer makes the compiler rebuild the
+// window base -- S2R tid, S2UR CgaCtaId, ULEA, LEA -- on every pop)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t popc8(uint32_t v) { return __popc(v & 0xffu); }   // get_bitcount :23-29
 
 // fetchChildOffset, kernel/kernel.cl:32-62.  rekursion==1 never needs its load (the walk stops there and
 // fetchColor ignores the node id), so none is issued.
-__device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct, uint32_t node, uint32_t before,
+// `enters_block` replaces the reference's test `!(nodeid_before & 256)` (:45): a bit-8 node whose parent is a normal node
+// is a block root, and block roots sit at tree depth D-6, i.e. exactly at rekursion == 6 (octree.h:245).
+constexpr int kBlockRootLevel = 6;
+__device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct, uint32_t node, bool enters_block,
                                                 uint32_t &local_root, uint32_t child, uint32_t child_test, int rekursion)
 {
     // word indices are summed in 32 bits (the pool is < 2^32 words): one IMAD.WIDE per load instead of a 64-bit chain
     uint32_t n = node >> 9, nadd = child;
     if (node & 256u) {
-        if (!(before & 256u)) { local_root = n << 6; n = 0; }
+        if (enters_block) { local_root = n << 6; n = 0; }
         n += local_root;
         nadd = popc8(node & ((child_test << 1) - 1u));
         if (rekursion <= 2) {                                             // the two byte-packed levels, once per ray
@@ -94,7 +101,7 @@ __device__ __forceinline__ uint32_t fetch_color(const uint32_t *__restrict__ oct
 
 // One primary ray for pixel (idx, idy): ray set-up of raycast_holes :639-663 / raycast_fine_2 :883-908,
 // CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
-// `stack` points at this thread's column of the shared [D+1][STRIDE] array (STRIDE = threads per CTA).
+// `stack` points at this thread's column of the shared [D+2][STRIDE] array (STRIDE = threads per CTA).
 template <int D, int STRIDE = kRayBlock>
 __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
@@ -126,28 +133,35 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     const float len2 = sqrtf(g2x * g2x + g2y * g2y + 1.0f);
 
     int ix = __float2int_rz(px), iy = __float2int_rz(py), iz = __float2int_rz(pz);
-    uint32_t nodeid = root, before = root, local_root = 0, node_test = 0;
+    uint32_t nodeid = root, local_root = 0, node_test = 0;
     int rekursion = D, lod = 1, x0ry = 0;
     float distance = 0.f, lodswitch = (float)(res_x * 2);          // res_x*LOD_ADJUST*2 :663
-    int guard = 1 << 20;                                           // never reached; bounds a corrupt octree
+    bool hit = false;
+    // Ancestors live in the shared stack: level r holds the node the ray is in at that level, levels D and D+1 the root
+    // (the reference's `rekursion==11 -> both = root`, :208).  The reference's nodeid_before is therefore not carried
+    // through the loop: outside a hit it is stack[rekursion+1], at a hit stack[rekursion].
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stack);
+    asm volatile("" : "+r"(sbase));                                   // opaque: keep it in a register, do not rematerialise
+    constexpr uint32_t kLevel = (uint32_t)STRIDE * 4u;                // bytes between two levels of one thread's column
+    sts_u32(sbase + D * kLevel, root);
+    sts_u32(sbase + (D + 1) * kLevel, root);
 
     // The reference's loop takes one of two branches per iteration (descend into an occupied child / step through an
     // empty cell).  Same per-ray sequence, arranged "while-while": the lanes of a warp first run their descents together,
     // then all step together, instead of paying for both branches on every trip once they fall out of phase.
+    // (No iteration guard: every step moves the ray onto a cell face, so the distance grows until :203 or :211 ends it,
+    // exactly as in the reference.)
     for (;;) {
         int cx, cy, cz;
-        bool hit = false;
         for (;;) {                                                     // descend while the child under the ray is occupied
             cx = ix >> rekursion; cy = iy >> rekursion; cz = iz >> rekursion;
             const int node_index = ((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) ^ sign_xyz;
             node_test = nodeid & (1u << node_index);
             if (!node_test) break;
-            const uint32_t tmp = nodeid;
-            nodeid = fetch_child(oct, nodeid, before, local_root, (uint32_t)node_index, node_test, rekursion);
-            before = tmp;
+            nodeid = fetch_child(oct, nodeid, rekursion == kBlockRootLevel, local_root, (uint32_t)node_index, node_test, rekursion);
             if (rekursion <= lod) { hit = true; break; }               // :172
             --rekursion;
-            stack[rekursion * STRIDE] = nodeid;
+            sts_u32(sbase + (uint32_t)rekursion * kLevel, nodeid);
         }
         if (hit) break;
         const float mx = (float)((cx + 1) << rekursion) - px;          // :181 step to the nearest face of the current cell
@@ -167,22 +181,19 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
         if (distance > kViewDistMax) break;                            // :203
         // (int)log2((float)x0r): floor(log2) for x0r>0, INT_MIN for 0  ->  "x0r < 2^rekursion" means stay in this node
         if ((x0r >> rekursion) != 0) {
-            rekursion = 32 - __clz(x0r);                               // rekursion_new + 1
-            if (rekursion >= D) { nodeid = before = root; }
-            else {
-                nodeid = stack[rekursion * STRIDE];
-                before = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
-            }
+            rekursion = 32 - __clz(x0r);                               // rekursion_new + 1  (<= D)
+            nodeid = lds_u32(sbase + (uint32_t)rekursion * kLevel);
             if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }    // :209
         }
-        if ((x0ry & kScaleMax) != 0 || !--guard) break;                // :211 the ray left the world through y
+        if ((x0ry & kScaleMax) != 0) break;                            // :211 the ray left the world through y
     }
 
     if (sign_xyz & 1) px = (float)kScaleMax - px;
     if (sign_xyz & 2) py = (float)kScaleMax - py;
     if (sign_xyz & 4) pz = (float)kScaleMax - pz;
 
-    const uint32_t before2 = (rekursion + 1 >= D) ? root : stack[(rekursion + 1) * STRIDE];
+    const uint32_t before2 = lds_u32(sbase + (uint32_t)(rekursion + 1) * kLevel);
+    const uint32_t before = hit ? lds_u32(sbase + (uint32_t)rekursion * kLevel) : before2;
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;

@@ -304,7 +304,7 @@ k_raycast_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const u
                 const uint32_t *__restrict__ idb, const uint32_t *__restrict__ size_ptr, uint32_t root,
                 int res_x, int res_y, int idbuf_size, RayCam cam)
 {
-    __shared__ uint32_t stack[(D + 1) * kRayBlock];
+    __shared__ uint32_t stack[(D + 2) * kRayBlock];
     const int idsize = (res_x / 16) * (res_y / 16);
     const int total = size_ptr ? (int)*size_ptr : idbuf_size;
     for (int id = blockIdx.x * kRayBlock + threadIdx.x; id < total; id += gridDim.x * kRayBlock) {
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kRayBlock)
 k_raycast_fine_2(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
                  uint32_t root, int res_x, int res_y, int gx, int gy, int add_x, int add_y, RayCam cam)
 {
-    __shared__ uint32_t stack[(D + 1) * kRayBlock];
+    __shared__ uint32_t stack[(D + 2) * kRayBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
     const int gx0 = blockIdx.x * 32 + lx, gy0 = blockIdx.y * 8 + ly;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kRayBlock)
 k_raycast_fine(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
                int res_x, int res_y, int gx, int gy, int frame, int add_x, int add_y, RayCam cam)
 {
-    __shared__ uint32_t stack[(D + 1) * kRayBlock];
+    __shared__ uint32_t stack[(D + 2) * kRayBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gx0 = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7), gy0 = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (gx0 >= gx || gy0 >= gy) return;
