@@ -110,6 +110,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this same
+    command (profiles/ncu_traffic.json, written by tools/dram_summary.py); None if there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -452,7 +462,7 @@ def main():
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom),
+                             "traffic": ncu_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom),
                              "avg_launch_ms": avg_ms, "octree_words_per_ray": L, "iterations_per_ray": iters}}
         # the same figure for the frame's dominant bandwidth kernel (the traversal kernels are latency bound)
         stream_k = [k for k in ("k_copy_colorize", "k_resolve_gather", "k_proj_scatter2", "k_memcpy", "k_proj_resolve") if k in prof]
@@ -461,7 +471,7 @@ def main():
             s_ms = prof[sk][0] / max(1, prof[sk][1])
             s_ach = alg[sk] / (s_ms * 1e-3) / 1e9
             line["roofline_streaming"] = {"kernel": sk, "bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
-                                          "traffic": None, "algorithmic_bytes_per_launch": alg[sk], "avg_launch_ms": s_ms}
+                                          "traffic": ncu_traffic(sk), "algorithmic_bytes_per_launch": alg[sk], "avg_launch_ms": s_ms}
         if not args.no_cpu_baseline and world == 1:
             r = cpu_arm(octree, root, steps=24, warmup=args.warmup, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

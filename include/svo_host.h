@@ -31,6 +31,15 @@ uint64_t        svo_octree_num_unique_voxels(svo_octree_t t);
 int             svo_octree_depth(svo_octree_t t);
 void            svo_octree_free(svo_octree_t t);
 
+/* The same array built ON THE DEVICE of the current context (svo_init first) and left there: a device-resident node pool,
+ * nothing is uploaded but the voxel stream.  Word for word the array of svo_octree_build().
+ * Returns the device buffer (use it as mem_octree, free it with svo_free); *root_out = octree_root_normal. */
+#ifndef SVO_B200_H
+typedef struct svo_mem_s *svo_mem_t;
+#endif
+svo_mem_t       svo_octree_build_device(size_t n, const uint32_t *x, const uint32_t *y, const uint32_t *z,
+                                        const uint32_t *rgba, int depth, uint32_t *root_out, uint64_t *num_unique_out);
+
 /* ---- voxel streams -------------------------------------------------------------------------------------- */
 size_t          svo_voxels_count(svo_voxels_t v);
 const uint32_t *svo_voxels_x(svo_voxels_t v);

@@ -11,19 +11,7 @@
 #include <string>
 #include <vector>
 
-void svo_fail(int code, const char *fmt, ...);
-
-#define CU_CHECK(expr)                                                                             \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess) svo_fail((int)_e, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
-    } while (0)
-
-struct svo_mem_s {
-    void *dptr;
-    size_t bytes;
-    int device;
-};
+#include "abi_types.h"
 
 using svo::FusedScratch;
 

@@ -20,6 +20,9 @@ namespace svo {
 constexpr uint32_t kHole = 0xffffff00u;       // kernel/kernel.cl:267
 constexpr float kViewDistMax = 400000.0f;     // VIEW_DIST_MAX kernel/kernel.cl:15
 constexpr int kRayBlock = 256;                // threads per CTA of the ray kernels
+#ifndef SVO_RAY_MINBLOCKS
+#define SVO_RAY_MINBLOCKS 1                   // __launch_bounds__ min CTAs per SM of the full-screen ray kernels (register budget)
+#endif
 
 struct RayCam {                               // arguments shared by raycast_holes / raycast_fine_2
     float m0x, m0y, m0z;                      // a_m0.xyz   camera position (world units)

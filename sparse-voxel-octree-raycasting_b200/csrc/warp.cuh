@@ -318,7 +318,7 @@ k_raycast_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const u
 // raycast_fine_2 (kernel/kernel.cl:846-942): the gx*gy rectangle at (add_x, add_y).  Each warp takes an
 // 8x4 pixel footprint; a CTA covers 32x8 pixels... (2x4 warps of 8x4... laid out 4 wide, 2 high).
 template <int D>
-__global__ void __launch_bounds__(kRayBlock)
+__global__ void __launch_bounds__(kRayBlock, SVO_RAY_MINBLOCKS)
 k_raycast_fine_2(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
                  uint32_t root, int res_x, int res_y, int gx, int gy, int add_x, int add_y, RayCam cam)
 {

@@ -12,7 +12,8 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsvo_b200.so")
+# SVO_B200_LIB: another build of the same library (kernel tuning experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("SVO_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsvo_b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(nvcc, sm_100a). There is no CPU fallback.")

@@ -85,6 +85,22 @@ def build_octree_voxels(vox, depth=11):
     return _finish(_build_voxels(vox.handle, depth))
 
 
+_build_device = _sig("svo_octree_build_device", _vp, _sz, _u32p, _u32p, _u32p, _u32p, _i, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64))
+
+
+def build_octree_device(x, y, z, rgba, depth=11):
+    """The same array as build_octree(), built on the GPU of the current context (ocl_init first) and left there:
+    -> (Mem usable as mem_octree, octree_root_normal, stats)."""
+    from . import ocl
+    x, y, z, rgba = (np.ascontiguousarray(a, dtype=np.uint32) for a in (x, y, z, rgba))
+    root, nu = C.c_uint32(), C.c_uint64()
+    h = _build_device(len(x), x, y, z, rgba, depth, C.byref(root), C.byref(nu))
+    ocl._check()
+    if not h:
+        raise RuntimeError("svo_octree_build_device failed")
+    return ocl.Mem(h, int(ocl._svo_mem_size(h))), int(root.value), dict(num_voxels=len(x), num_unique=int(nu.value))
+
+
 def rle4_load(path, palette=0, addx=0, addy=0, addz=0):
     return Voxels(_rle4_load(os.fsencode(path), palette, addx, addy, addz))
 

@@ -444,3 +444,31 @@ def test_disabled_kernel_fine(svo, orc, world, frame):
     assert np.array_equal(mb.to_numpy(np.uint32), exp_b.view(np.uint32))
     for m in (mo, ms, mb):
         m.free()
+
+
+@pytest.mark.parametrize("name,depth", [("small_world", 11), ("duplicates", 11), ("single", 11), ("cloud", 11), ("dense", 11),
+                                        ("zero_colour", 11), ("terrain14", 14)])
+def test_device_octree_builder(svo, orc, name, depth):
+    """svo_octree_build_device: the node pool built on the GPU is, word for word, the array of the
+    reference's set_voxel + convert_tree_blocks (via the oracle), including duplicate insertions, zero colour words, a
+    single voxel and OCTREE_DEPTH 14."""
+    rng = np.random.RandomState(4)
+    sc = {"small_world": scenes.small_world, "duplicates": scenes.duplicates, "single": scenes.single_voxel,
+          "cloud": lambda: scenes.random_cloud(20000, 0, 2048, 9), "dense": lambda: scenes.cube(1000, 1000, 1000, 70),
+          "zero_colour": lambda: (np.array([7, 8, 9], np.uint32), np.array([1, 1, 1], np.uint32), np.array([5, 5, 5], np.uint32),
+                                  np.array([0x11, 0, 0x21], np.uint32)),
+          "terrain14": lambda: scenes.concat(scenes.terrain(256, 5000, 9000, height=300, base=8000, seed=2),
+                                             scenes.random_cloud(30000, 0, 16384, 4))}[name]()
+    orc.lib.orc_set_depth(depth)
+    try:
+        exp, root = orc.build_octree(*sc)
+    finally:
+        orc.lib.orc_set_depth(11)
+    mem, got_root, st = svo.scene.build_octree_device(*sc, depth=depth)
+    try:
+        assert got_root == root
+        assert mem.size == exp.nbytes
+        assert np.array_equal(mem.to_numpy(), exp)
+        assert st["num_unique"] <= len(sc[0])
+    finally:
+        mem.free()

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Condense an ncu report (.ncu-rep) into the per-kernel table kept under profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.md"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [traffic.json] > profiles/<name>.md
+With a second argument the per-kernel average of dram__bytes_read.sum + dram__bytes_write.sum per launch is merged into
+that JSON file ({kernel: {"dram_bytes_per_launch": ...}}): bench.py reads profiles/ncu_traffic.json for roofline.traffic."""
 import csv
 import io
 import subprocess
@@ -42,6 +44,20 @@ def main():
                 pass
             vals.append(v)
         print("| " + r[ki].split("(")[0].replace("void ", "") + " | " + " | ".join(vals) + " |")
+    if len(sys.argv) > 2:
+        import json, os
+        UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        acc = {}
+        ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        for r in rows[2:]:
+            k = r[ki].split("(")[0].replace("void ", "").replace("svo::", "").split("<")[0]
+            b = float(r[ir].replace(",", "")) * UNIT.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * UNIT.get(units[iw], 1.0)
+            acc.setdefault(k, []).append((b, float(r[it].replace(",", ""))))
+        out = json.load(open(sys.argv[2])) if os.path.exists(sys.argv[2]) else {}
+        for k, v in acc.items():
+            out[k] = {"dram_bytes_per_launch": sum(x[0] for x in v) / len(v), "launches_profiled": len(v),
+                      "source": os.path.basename(rep) + " (ncu --set full, caches flushed before each replay)"}
+        json.dump(out, open(sys.argv[2], "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
