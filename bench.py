@@ -225,6 +225,28 @@ def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, fr
     return out
 
 
+def builder_bench(svo, path, local_rank):
+    """the compact octree of the bench scene built by the host builder and by the device builder
+    (svo_octree_build_device: the node pool is built on the GPU and stays there); the two arrays must be identical."""
+    ocl = svo.ocl
+    vox = svo.scene.rle4_load(path)
+    x, y, z, c = vox.arrays()
+    vox.free()
+    t0 = time.perf_counter()
+    words, root, _ = svo.scene.build_octree(x, y, z, c, depth=11)
+    host_s = time.perf_counter() - t0
+    ocl.ocl_init(local_rank)
+    svo.scene.build_octree_device(x[:1000], y[:1000], z[:1000], c[:1000], depth=11)[0].free()      # CUDA / CUB warm-up
+    t0 = time.perf_counter()
+    mem, droot, st = svo.scene.build_octree_device(x, y, z, c, depth=11)
+    dev_s = time.perf_counter() - t0
+    same = bool(droot == root and mem.size == words.nbytes and np.array_equal(mem.to_numpy(), words))
+    mem.free()
+    ocl.ocl_exit()
+    return {"voxels": int(len(x)), "host_builder_s": round(host_s, 3), "device_builder_s": round(dev_s, 3),
+            "identical": same, "host_threads": os.cpu_count(), "includes": "device: H2D of the voxel stream (16 B/voxel) + sort + emit + normal nodes"}
+
+
 def terrain14_bench(svo, args, frames=64):
     """BASELINE.json config 4: fBm fractal terrain at OCTREE_DEPTH 14 (4096^2 columns of a 16384^3 world, 3-voxel shell),
     the flythrough at 8x translation and 4x rotation speed (high hole fraction), 1920x1024, fused frame."""
@@ -484,6 +506,7 @@ def main():
         extras["bands_3840x2160"] = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args)
         if world == 1:
             extras["terrain_depth14"] = terrain14_bench(svo, args)
+            extras["octree_build"] = builder_bench(svo, path, local_rank)
     if rank == 0:
         line.update(extras)
         print(json.dumps(line))
