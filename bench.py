@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
-        try:                                   # NVML in-process: a sample every ~5 ms (the timed region is ~50 ms)
+        try:                                   # NVML in-process: a sample every ~20 ms (NVML queries take driver locks: sampling faster stalls the launches being timed)
             import pynvml as nv
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)]
                                     + ["Active" if r & b else "Not Active" for _, b in bits])
-                time.sleep(0.005)
+                time.sleep(0.02)
             return
         except Exception:
             pass
@@ -391,9 +391,10 @@ def main():
     sync_all()
     t0 = time.perf_counter()
     for f in range(args.warmup, total):
-        # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame, read back
-        # on the copy stream while the next frame renders.  The caller owns frame f-1 after present_wait.
-        k = rc.draw_present(P[f], host_frames)
+        # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame as R,G,B
+        # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frame renders.  The
+        # caller owns frame f-1 after present_wait.
+        k = rc.draw_present(P[f], host_frames, rgb24=True)
         if f > args.warmup:
             ocl.present_wait(k ^ 1)
     ocl.present_wait(k)
@@ -401,7 +402,7 @@ def main():
     host_frame = host_frames[k]
     sampler.stop_flag = True
     sampler.join()
-    checksum = int(np.frombuffer(host_frame, dtype=np.uint32, count=n).sum(dtype=np.uint64))
+    checksum = int(np.frombuffer(host_frame, dtype=np.uint8, count=n * 3).sum(dtype=np.uint64))
 
     # ---- full-screen primary rays (BASELINE.json config 1): raycast_fine_2 over the whole screen ----
     ray_ms = []
@@ -461,11 +462,13 @@ def main():
                "k_counthole": 4.0 * n, "k_writeids": 4.0 * n, "k_sumids": 8.0 * (n // 256),
                "k_raycast_fine_2": (4.0 * L + 16.0) * tile_rays, "k_raycast_holes": (4.0 * L + 20.0) * H,
                # fused frame
-               "k_proj_scatter2": 4.0 * nsrc_px + 16.0 * V + 8.0 * V,            # colour words, positions, one 8-byte key RMW each
-               "k_resolve_gather": 8.0 * n + 20.0 * W + 20.0 * W + 4.0 * (n - W) + 8.0 * W + 4.0 * H,   # keys in, gather, dest out, hole words, re-arm, ids
+               # exact mode: the pass also carries the previous frame's cache copy (20N in, 20N out) and reads buffer 0 only
+               "k_proj_scatter2": (40.0 * n if args.mode == "fused" else 4.0 * nsrc_px + 16.0 * V) + 8.0 * V,   # + one 8-byte key RMW each
+               # keys in, gather, dest out, hole words, re-arm, ids, colorized word per pixel
+               "k_resolve_gather": 8.0 * n + 20.0 * W + 20.0 * W + 4.0 * (n - W) + 8.0 * W + 4.0 * H + 4.0 * n,
                "k_rays_tile": (4.0 * L + 16.0) * tile_rays, "k_rays_holes": (4.0 * L + 20.0) * H,
-               "k_copy_colorize": (44.0 if args.mode == "fused" else 8.0) * n,    # 20N in, 20N out, 4N image
-               "k_fill_compute": 28.0 * resid_px, "k_apply_patches": 12.0 * resid_px}
+               "k_copy_colorize": 40.0 * n,                                       # only when the host observes the buffers
+               "k_fill_list": 28.0 * resid_px, "k_apply_patches": 12.0 * resid_px}
         d_ms, d_cnt = prof[dom]
         avg_ms = d_ms / max(1, d_cnt)
         achieved = alg.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
@@ -479,7 +482,7 @@ def main():
                                       "no L2 flush between frames (a frame reads what the previous frame wrote, as in the real pipeline)",
                            "hole_fraction_last_frame": hole_frac},
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
-                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 4,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum},
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},

@@ -93,6 +93,9 @@ void   svo_copy_to_host_async(void *dst, svo_mem_t src, size_t size, size_t srco
  * immediately (give it another colorize target).  slot 0..3; svo_present_wait(slot) blocks until that copy has landed. */
 void   svo_present_async(void *host_dst, svo_mem_t src, size_t size, int slot);
 void   svo_present_wait(int slot);
+/* the same, as 24-bit R,G,B bytes (the payload of a binary PPM, 3 bytes per pixel instead of the PBO's 4): the frame is
+ * packed on the device first, so a quarter less crosses PCIe.  `host_dst` receives npixels*3 bytes. */
+void   svo_present_rgb24_async(void *host_dst, svo_mem_t src, size_t npixels, int slot);
 
 /* ---- fused frame (B200-native fast path; same results as the 13-launch sequence of
  *      raycast_draw, src/raycast.h:147-438, without the mid-frame host readback) ------------------ */
@@ -120,6 +123,13 @@ void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t idb
 int  svo_frame_idbuf_size(void);
 /* buffer index (0 or 2) the last fused frame was rendered into; always 0 without SVO_FRAME_PINGPONG */
 int  svo_frame_last_slot(void);
+/* Number of fused frames so far whose reprojection pass carried the previous frame's cache copy.  svo_frame_fused leaves
+ * the copy of src/raycast.h:394-405 pending; when the next frame follows before anything observed or changed a buffer,
+ * its reprojection reads the previous frame out of buffer 0 once, stores it into buffer 2 and projects it in the same
+ * pass.  Any read-back, launch, memcpy/memset, svo_event_record or svo_end_all_kernels issues the plain copy first, so
+ * every observation finds buffer 2 as the reference leaves it.  Diagnostic: lets a test prove which schedule produced
+ * the buffers it compares. */
+unsigned long long svo_frame_deferred_count(void);
 
 /* ---- screen bands across the GPUs of one box (extension: the reference is single-device, src/ocl.h:89,127,140) ----
  * The screen is cut into stripes of `stripe_rows` rows (rounded up to a multiple of the 16-row hole block; <= 0 selects

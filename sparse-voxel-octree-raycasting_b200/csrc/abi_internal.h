@@ -21,6 +21,16 @@ struct svo_ctx_s {
     cudaStream_t stream2 = nullptr;         // tile-refresh rays of the fused frame run here, concurrently
     cudaEvent_t ev_frame_done = nullptr, ev_tile_done = nullptr;
     cudaEvent_t ev_copy_done = nullptr, ev_fill_done = nullptr;
+    // lazy cache copy (svo_frame_fused): the end-of-frame copy buffer 0 -> 2 stays pending and is fused into the next
+    // frame's reprojection pass; colorize + gap filter run on a third stream right after the rays
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_scatter_done = nullptr, ev_rays_done = nullptr;
+    bool copy_pending = false;              // buffer 2 does not yet hold the last frame (materialize_copy)
+    uint32_t *pend_src_s = nullptr, *pend_dst_s = nullptr;   // the pending copy: colour words ...
+    float *pend_src_b = nullptr, *pend_dst_b = nullptr;      // ... and positions
+    uint32_t pend_n = 0;
+    int pend_res_x = 0;
+    uint64_t frames_from0 = 0;              // frames whose reprojection carried the previous frame's copy (svo_frame_deferred_count)
     svo::PatchList patch = {nullptr};       // gap-filter results of the last fused frame (k_fill_list on stream2)
     unsigned int *patch_count = nullptr;    // the residual-hole counter and list they belong to
     uint32_t *patch_resid = nullptr;
@@ -38,7 +48,7 @@ struct svo_ctx_s {
     size_t snap_words = 0;
     const void *l2_pinned = nullptr;        // octree currently covered by the persisting-L2 access window
     size_t l2_persist_max = 0, l2_window_max = 0;
-    FusedScratch fs = {nullptr, nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
+    FusedScratch fs = {nullptr, nullptr, nullptr, nullptr, nullptr};   // fused-frame scratch (fused.cuh)
     size_t fs_ctas = 0, fs_pixels = 0;
     uint32_t epoch = 0;
     uint64_t launches = 0;
@@ -46,6 +56,8 @@ struct svo_ctx_s {
     cudaEvent_t events[16] = {};
     cudaStream_t copy_stream = nullptr;     // svo_present_async: frame read-back overlapped with the next frame
     cudaEvent_t present_ready[4] = {}, present_done[4] = {};
+    uint32_t *rgb_stage[4] = {};            // svo_present_rgb24_async: packed frame per slot
+    size_t rgb_stage_bytes[4] = {};
     // per-kernel profiling (svo_profile_*)
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };

@@ -339,7 +339,7 @@ k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const 
         if (lx >= gx || lr >= lrows) continue;
         const int idx = lx + add_x, idy = m.global_row(lr);
         if (idy < add_y || idy >= add_y + gy || idx >= m.res_x || idy >= m.res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 

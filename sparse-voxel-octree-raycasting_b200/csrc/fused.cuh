@@ -32,10 +32,11 @@ struct FusedScratch {
     unsigned int *counters;           // [0] ticket, [1] done, [4..7] residual-hole counts (rotating over 4 frames)
     uint32_t *resid;                  // pixel offsets of the hole pixels left for the gap filter
     unsigned int *resid_count;        // this frame's counter
+    uint32_t *tex;                    // != nullptr: every kernel that writes a colour word also writes its colorized form here
 };
 
-struct PatchList {                    // gap-filter results: filtered word per entry of the residual-hole list
-    uint32_t *value;                  // value[i] belongs to pixel resid[i]; kHole = nothing within reach
+struct PatchList {                    // gap-filter results, one word per pixel, defined for the in-bounds hole pixels
+    uint32_t *value;                  // value[p] = filtered word of hole pixel p; kHole = nothing within reach
 };
 
 struct Rect { int x0, y0, x1, y1; };  // tile-refresh rectangle [x0,x1) x [y0,y1) in pixels
@@ -68,6 +69,38 @@ __device__ __forceinline__ bool proj_point_fast(const ProjCam &c, float pcx, flo
     return !(scrx >= res_x - 1 || scrx < 0 || scry >= res_y - 1 || scry < 0);
 }
 
+// Small-gap filter (raycast_fillhole2, kernel.cl:404-470), snapshot semantics.  `snap` holds the pre-filter image of
+// pixels [0, n) and is not modified while a filter kernel runs; linear offsets >= n (the 5x5 search near the last rows)
+// read `beyond`, the words that follow the image in the reference's layout.
+struct SnapView {
+    const uint32_t *snap, *beyond; int n;
+    __device__ __forceinline__ uint32_t operator[](int i) const { return i < n ? snap[i] : beyond[i]; }
+};
+__device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, int res_x)
+{
+    const uint32_t c1 = s[ofs + 1], c2 = s[ofs - 1], c3 = s[ofs + res_x], c4 = s[ofs - res_x];
+    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
+        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
+    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
+    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+    uint32_t col = c1;                                   // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
+    if (col == kHole) col = c3;                          // i = 2
+    if (col == kHole) col = s[ofs + 1 + res_x];          // i = 3
+    if (col == kHole) {
+        // 5x5 search, x offset outer / y offset inner (:461-467): first valid word in scan order.  All 25 loads are issued
+        // before the first test -- one memory round trip instead of up to 25 dependent ones (the words lie inside the
+        // reference's 4-buffer array for every pixel the filter touches, :416)
+        uint32_t v[25];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) v[i * 5 + j] = s[ofs + (i - 2) + (j - 2) * res_x];
+#pragma unroll
+        for (int k = 0; k < 25; ++k) if (col == kHole) col = v[k];
+    }
+    return col;
+}
+
 // sources: `nsrc` pixels starting at pixel offset `src0` (exact mode: buffers 1 and 2 = 2N pixels from N; ascending
 // offset is the launch order of the reference, which is what breaks depth ties).
 // The reference also turns a source pixel that leaves the view into a hole (kernel.cl:559-562).  Inside the frame that
@@ -75,18 +108,34 @@ __device__ __forceinline__ bool proj_point_fast(const ProjCam &c, float pcx, flo
 // (ping-pong: the slot is rewritten before it is read again), and the resolve pass only gathers sources that produced a
 // key.  It is therefore not issued here (the launch-by-launch raycast_proj of warp.cuh does it), which makes this kernel
 // read-only on the cache.  One source per thread, short-lived CTAs: launches of the second stream slip in between.
+//
+// Lazy cache copy (`copy_s` != nullptr).  The reference ends every frame with buffer 0 -> buffer 2 (src/raycast.h:394-405)
+// and starts the next one by reading buffer 2 back.  svo_frame_fused leaves that copy pending; when the next frame
+// follows with nothing having observed the buffers in between, this kernel reads the previous frame out of buffer 0
+// ONCE (20 B/pixel), stores it into buffer 2 and projects it in the same pass.  `key_bias` (2N) makes the keys name the
+// pixels of buffer 2, which is where the resolve pass gathers from -- same words, same keys as copy-then-project.
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
-                int res_x, int res_y, unsigned int src0, unsigned int nsrc, ProjCam c)
+                int res_x, int res_y, unsigned int src0, unsigned int nsrc, unsigned int key_bias, ProjCam c,
+                uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b)
 {
     const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nsrc) return;
     const uint32_t srcofs = q + src0;
-    if (__ldg(screen + srcofs) == kHole) return;
-    const float4 pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+    const uint32_t word = __ldg(screen + srcofs);
+    float4 pc;
+    if (copy_s) {                                        // the copy takes every pixel, holes and their stale positions included
+        pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+        copy_s[q] = word;
+        copy_b[q] = pc;
+        if (word == kHole) return;
+    } else {
+        if (word == kHole) return;
+        pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+    }
     int sx, sy; float phz;
     if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) return;
-    atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);
+    atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (srcofs + key_bias));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -143,9 +192,15 @@ k_resolve_gather(const GatherArgs a)
                 const float4 pc = *reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4);
                 const float phz = (pc.x - a.c.m0x) * a.c.mzx + (pc.y - a.c.m0y) * a.c.mzy + (pc.z - a.c.m0z) * a.c.mzz;
                 if (inr) dback[p * 4 + 3] = phz;
-                else { dscreen[p] = (uint32_t)(k >> 32) + (col & 255u); *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz); }
+                else {
+                    const uint32_t w = (uint32_t)(k >> 32) + (col & 255u);
+                    dscreen[p] = w;
+                    if (a.s.tex) a.s.tex[p] = colorize_word(w);
+                    *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz);
+                }
             } else if (!inr) {
                 dscreen[p] = kHole;
+                if (a.s.tex) a.s.tex[p] = colorize_word(kHole);
                 if (x > 1 && y > 1 && x < res_x - 1 && y < res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
             }
         }
@@ -224,8 +279,13 @@ k_resolve_gather(const GatherArgs a)
                         else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
                     }
                 }
-                if (even && !inr[2 * r] && !inr[2 * r + 1]) *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
-                else { if (!inr[2 * r]) dscreen[p] = out[0]; if (!inr[2 * r + 1]) dscreen[p + 1] = out[1]; }
+                if (even && !inr[2 * r] && !inr[2 * r + 1]) {
+                    *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
+                    if (a.s.tex) *reinterpret_cast<uint2 *>(a.s.tex + p) = make_uint2(colorize_word(out[0]), colorize_word(out[1]));
+                } else {
+                    if (!inr[2 * r]) { dscreen[p] = out[0]; if (a.s.tex) a.s.tex[p] = colorize_word(out[0]); }
+                    if (!inr[2 * r + 1]) { dscreen[p + 1] = out[1]; if (a.s.tex) a.s.tex[p + 1] = colorize_word(out[1]); }
+                }
             }
         }
         // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
@@ -324,7 +384,7 @@ k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 
@@ -343,7 +403,7 @@ k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint3
         if (lx >= gx || ly >= gy) continue;
         const int idx = lx + add_x, idy = ly + add_y;
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 
@@ -376,34 +436,7 @@ k_copy_colorize(const uint32_t *__restrict__ src_s, const float4 *__restrict__ s
     }
 }
 
-// Small-gap filter (raycast_fillhole2, kernel.cl:404-470) on the listed hole pixels, snapshot semantics.  `snap` holds the
-// pre-filter image of pixels [0, n) and is not modified while this runs (exact mode: the cache copy in buffer 2, which the
-// next frame only reads; ping-pong: the destination slot); linear offsets >= n (the 5x5 search near the last rows) read
-// `beyond`, the words that follow the image in the reference's layout.  The filtered word goes to the colorized image at
-// once and into value[i] for the in-place write (k_apply_patches).
-struct SnapView {
-    const uint32_t *snap, *beyond; int n;
-    __device__ __forceinline__ uint32_t operator[](int i) const { return i < n ? snap[i] : beyond[i]; }
-};
-__device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, int res_x)
-{
-    const uint32_t c1 = s[ofs + 1], c2 = s[ofs - 1], c3 = s[ofs + res_x], c4 = s[ofs - res_x];
-    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
-        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
-    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
-    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
-    uint32_t col = c1;                                   // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
-    if (col == kHole) col = c3;                          // i = 2
-    if (col == kHole) col = s[ofs + 1 + res_x];          // i = 3
-    if (col == kHole)
-        for (int i = -2; i < 3 && col == kHole; ++i)
-            for (int j = -2; j < 3; ++j) {
-                if (col != kHole) break;
-                col = s[ofs + i + j * res_x];
-            }
-    return col;
-}
-
+// The gap filter on the listed hole pixels only (~1-3 % of the frame); third stream, beside the next frame's reprojection.
 __global__ void __launch_bounds__(256)
 k_fill_list(SnapView view, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid, const unsigned int *__restrict__ resid_count,
             PatchList patch, int res_x)
@@ -411,12 +444,11 @@ k_fill_list(SnapView view, uint32_t *__restrict__ tex, const uint32_t *__restric
     const unsigned int cnt = resid_count[0];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int p = (int)resid[i];
-        uint32_t f = kHole;
         if (view[p] == kHole) {                          // else: listed before a ray filled it
-            f = fillhole2_view(view, p, res_x);
+            const uint32_t f = fillhole2_view(view, p, res_x);
             if (f != kHole && tex) tex[p] = colorize_word(f);
+            patch.value[p] = f;
         }
-        patch.value[i] = f;
     }
 }
 
@@ -428,8 +460,10 @@ k_apply_patches(uint32_t *__restrict__ out_s, const uint32_t *__restrict__ resid
 {
     const unsigned int cnt = resid_count[0];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const uint32_t f = patch.value[i];
-        if (f != kHole) out_s[resid[i]] = f;
+        const uint32_t p = resid[i];
+        if (out_s[p] != kHole) continue;                 // listed before a ray filled it: never a filter target
+        const uint32_t f = patch.value[p];
+        if (f != kHole) out_s[p] = f;
     }
 }
 

@@ -102,6 +102,19 @@ __device__ __forceinline__ uint32_t fetch_color(const uint32_t *__restrict__ oct
     return ldg(oct + n + nadd);
 }
 
+// raycast_colorize (kernel/kernel.cl:944-974) of one word; here because the fused frame colorizes at the producers
+__device__ __forceinline__ uint32_t colorize_word(uint32_t word)
+{
+    const int a = (int)word;
+    const int t = a & 3;
+    const float i = (float)(a & (255 - 7));
+    const float tr = t == 0 ? 1.0f : t == 1 ? 1.0f : t == 2 ? 1.5f : 0.2f;       // color_tab :959-963
+    const float tg = t == 0 ? 1.0f : t == 1 ? 0.7f : t == 2 ? 0.8f : 0.8f;
+    const float tb = t == 0 ? 1.0f : t == 1 ? 0.3f : t == 2 ? 0.1f : 0.2f;
+    const int r = min(__float2int_rz(i * tr), 255), g = min(__float2int_rz(i * tg), 255), b = min(__float2int_rz(i * tb), 255);
+    return (uint32_t)(b + g * 256 + r * 65536);
+}
+
 // One primary ray for pixel (idx, idy): ray set-up of raycast_holes :639-663 / raycast_fine_2 :883-908,
 // CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
 // `stack` points at this thread's column of the shared [D+2][STRIDE] array (STRIDE = threads per CTA).
@@ -109,7 +122,8 @@ template <int D, int STRIDE = kRayBlock>
 __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
                                             int idx, int idy, const RayCam &c, uint32_t *stack,
-                                            unsigned int *resid_count = nullptr, uint32_t *resid = nullptr)
+                                            unsigned int *resid_count = nullptr, uint32_t *resid = nullptr,
+                                            uint32_t *__restrict__ tex = nullptr)
 {
     constexpr int kScaleMax = 1 << (D + 1);            // SCALE_MAX :19
     constexpr int kDepthAnd = (1 << D) - 1;            // OCTREE_DEPTH_AND :13
@@ -200,6 +214,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;
+    if (tex) tex[ofs] = colorize_word(0xff000000u + col);              // fused frame: no separate colorize pass
     // a traced word can coincide with the hole marker (unmasked colour 0x00ffff00): the gap filter must see it
     if (resid && 0xff000000u + col == kHole && idx > 1 && idy > 1 && idx < res_x - 1 && idy < res_y - 1)
         resid[atomicAdd(resid_count, 1u)] = (uint32_t)ofs;

@@ -43,8 +43,21 @@ svo_ctx_t svo_need_ctx() { return need_ctx(); }
 // the filter's in-place write into buffer 0 pending: inside the pipeline nothing reads it (the next frame rewrites buffer
 // 0).  Whenever the host could observe buffer 0 -- a sync, a read-back, a launch through the kernel API -- the pending
 // write is issued first, so every observation sees what the reference sequence leaves.
+static inline int bw_grid(svo_ctx_t c, size_t items, int block, int per_sm);
+// The lazy cache copy: svo_frame_fused leaves buffer 0 -> buffer 2 (src/raycast.h:394-405) pending so that the next
+// frame's reprojection pass can carry it (k_proj_scatter2 reads the frame once for both).  Anything that observes or
+// changes a buffer, or times the stream, gets the plain copy issued first.
+static void materialize_copy(svo_ctx_t c)
+{
+    if (!c->copy_pending) return;
+    c->copy_pending = false;
+    LaunchScope ls(c, "k_copy_colorize");
+    svo::k_copy_colorize<<<bw_grid(c, (size_t)c->pend_n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
+        c->pend_src_s, reinterpret_cast<const float4 *>(c->pend_src_b), c->pend_dst_s, reinterpret_cast<float4 *>(c->pend_dst_b), nullptr, (int)c->pend_n);
+}
 static void flush_patches(svo_ctx_t c)
 {
+    materialize_copy(c);                             // before the filter's in-place words: buffer 2 is the pre-filter frame
     if (c->fill_outstanding) {                       // the colorized image / patch list of the last frame are still being written
         CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0));
         c->fill_outstanding = false;
@@ -82,12 +95,15 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     c->num_sms = prop.multiProcessorCount;
     int prio_lo = 0, prio_hi = 0;
     CU_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, getenv("SVO_MAIN_HI") ? prio_hi : prio_lo));
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_fill_done, cudaEventDisableTiming));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, getenv("SVO_S3_LO") ? prio_lo : prio_hi));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_scatter_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_rays_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     return c;
@@ -105,11 +121,15 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     if (c->fs.resid) cudaFree(c->fs.resid);
     cudaStreamSynchronize(c->stream2);
     cudaStreamDestroy(c->stream2);
+    cudaStreamSynchronize(c->stream3);
+    cudaStreamDestroy(c->stream3);
+    cudaEventDestroy(c->ev_scatter_done); cudaEventDestroy(c->ev_rays_done);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
     cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_fill_done);
     if (c->patch.value) cudaFree(c->patch.value);
     for (auto &e : c->events) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (auto &r : c->rgb_stage) if (r) cudaFree(r);
     for (auto &e : c->present_ready) if (e) cudaEventDestroy(e);
     for (auto &e : c->present_done) if (e) cudaEventDestroy(e);
     for (auto &r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -235,6 +255,54 @@ extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, in
     CU_CHECK(cudaMemcpyAsync(host_dst, src->dptr, size, cudaMemcpyDeviceToHost, c->copy_stream));
     CU_CHECK(cudaEventRecord(c->present_done[slot], c->copy_stream));
 }
+// 0x00RRGGBB words -> R,G,B bytes; four pixels (16 B) in, three words (12 B) out per thread
+__global__ void __launch_bounds__(256) k_pack_rgb24(const uint32_t *__restrict__ tex, uint32_t *__restrict__ out, size_t n)
+{
+    const size_t quads = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 w = reinterpret_cast<const uint4 *>(tex)[i];
+        auto rgb = [](uint32_t v) { return ((v >> 16) & 255u) | (v & 0xff00u) | ((v & 255u) << 16); };   // byte order R,G,B
+        const uint32_t a = rgb(w.x), b = rgb(w.y), c = rgb(w.z), d = rgb(w.w);
+        out[3 * i] = a | (b << 24);
+        out[3 * i + 1] = (b >> 8) | (c << 16);
+        out[3 * i + 2] = (c >> 16) | (d << 8);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {                      // 1..3 trailing pixels, byte stores
+        const size_t p = (quads << 2) + threadIdx.x;
+        const uint32_t v = tex[p];
+        uint8_t *o = reinterpret_cast<uint8_t *>(out) + 3 * p;
+        o[0] = (uint8_t)(v >> 16); o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)v;
+    }
+}
+
+extern "C" void svo_present_rgb24_async(void *host_dst, svo_mem_t src, size_t npixels, int slot)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!src || npixels * 4 > src->bytes || slot < 0 || slot >= 4) { svo_fail(-108, "svo_present_rgb24_async: bad arguments"); return; }
+    if (!c->copy_stream) {
+        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) {
+            CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
+            CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t bytes = npixels * 3;
+    if (c->rgb_stage_bytes[slot] < bytes + 16) {
+        if (c->rgb_stage[slot]) { CU_CHECK(cudaStreamSynchronize(c->copy_stream)); CU_CHECK(cudaFree(c->rgb_stage[slot])); }
+        CU_CHECK(cudaMalloc(&c->rgb_stage[slot], bytes + 16));
+        c->rgb_stage_bytes[slot] = bytes + 16;
+    }
+    CU_CHECK(cudaEventRecord(c->present_ready[slot], c->stream));
+    CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->present_ready[slot], 0));
+    if (c->fill_event_valid) CU_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_fill_done, 0));   // the gap filter's pixels
+    {
+        LAUNCH_ON(c, "k_pack_rgb24", c->copy_stream);
+        k_pack_rgb24<<<bw_grid(c, npixels / 4 + 1, 256, 8), 256, 0, c->copy_stream>>>((const uint32_t *)src->dptr, c->rgb_stage[slot], npixels);
+    }
+    CU_CHECK(cudaMemcpyAsync(host_dst, c->rgb_stage[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU_CHECK(cudaEventRecord(c->present_done[slot], c->copy_stream));
+}
 extern "C" void svo_present_wait(int slot)
 {
     svo_ctx_t c = need_ctx();
@@ -248,6 +316,10 @@ extern "C" void svo_event_record(int slot)
     svo_ctx_t c = need_ctx();
     if (!c || slot < 0 || slot >= 16) return;
     if (!c->events[slot]) CU_CHECK(cudaEventCreate(&c->events[slot]));
+    // the event covers all the work of the frames queued so far: the pending cache copy of the last fused frame is issued
+    // now, and the stream is ordered behind its colorize / gap filter on the side stream
+    materialize_copy(c);
+    if (c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
     CU_CHECK(cudaEventRecord(c->events[slot], c->stream));
 }
 extern "C" float svo_event_elapsed_ms(int a, int b)
@@ -264,6 +336,7 @@ static void prof_flush(svo_ctx_t c)
     if (c->prof_pending.empty()) return;
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
+    CU_CHECK(cudaStreamSynchronize(c->stream3));
     c->timeline.clear();
     for (auto &r : c->prof_pending) {
         float ms = 0.f, t0 = 0.f;
@@ -732,6 +805,7 @@ extern "C" void svo_end_all_kernels(void)                             // src/ocl
     flush_patches(c);
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
+    CU_CHECK(cudaStreamSynchronize(c->stream3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -764,7 +838,10 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     ensure_key(c, n);
     ensure_fused_scratch(c, ncta + 64, 2 * (size_t)n);                     // two residual-hole lists, alternating frames
     if (c->patch_pixels < n) {
-        if (c->patch.value) { CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaFree(c->patch.value)); }
+        if (c->patch.value) {
+            CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaStreamSynchronize(c->stream3));
+            CU_CHECK(cudaFree(c->patch.value));
+        }
         CU_CHECK(cudaMalloc(&c->patch.value, (size_t)n * 4));
         c->patch_pixels = n;
     }
@@ -783,14 +860,28 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const int add_x = (res_x / 8) * (frame & 7), add_y = (res_y / 4) * ((frame >> 3) & 3);   // :363-364
     const int gx = (int)svo_round_up(16, res_x / 8), gy = (int)svo_round_up(16, res_y / 4);
     const Rect tile = {add_x, add_y, add_x + gx < res_x ? add_x + gx : res_x, add_y + gy < res_y ? add_y + gy : res_y};
-    const bool overlap = !getenv("SVO_NO_OVERLAP");
+    static const bool overlap = !getenv("SVO_NO_OVERLAP");
+    static const bool lazy_copy = !getenv("SVO_NO_LAZY_COPY");
     c->epoch = (c->epoch + 1) & 0x3fffffffu;
     if (c->epoch == 0) c->epoch = 4;                                       // keeps the mod-4 counter rotation in step
     FusedScratch fs = c->fs;                                               // this frame's view of the scratch
-    fs.resid = c->fs.resid + (size_t)(c->epoch & 1u) * n;                  // the other list may still be read (second stream)
+    fs.resid = c->fs.resid + (size_t)(c->epoch & 1u) * n;                  // the other list may still be read (third stream)
     fs.resid_count = c->fs.counters + 4 + (c->epoch & 3u);                 // rotating: re-armed two frames ahead
     unsigned int *next_resid_count = c->fs.counters + 4 + ((c->epoch + 2) & 3u);   // while the next frame fills another one
+    // :429-437 colorize at the producers: the resolve pass and the rays store the colorized word next to the colour word
+    // (4 B/pixel on top of their 20), so there is no colorize pass; the gap filter adds its pixels afterwards
+    uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
+    const bool lazy = lazy_copy && !pingpong;
+    fs.tex = (lazy || pingpong) ? tex : nullptr;
 
+    // Lazy cache copy (exact mode).  The previous fused frame left buffer 0 -> 2 pending (materialize_copy).  If nothing
+    // has observed the buffers since, buffer 0 still holds that frame, and this frame's reprojection pass reads it there
+    // once for both purposes: it stores the words into buffer 2 (the copy) and projects them (keys biased by 2N name the
+    // pixels of buffer 2, which the resolve pass gathers from).  Otherwise the plain copy is issued first.
+    const bool from0 = c->copy_pending && !pingpong && frame >= 2 && c->pend_n == n && c->pend_res_x == res_x &&
+                       c->pend_src_s == screen && c->pend_src_b == back;
+    if (!from0) materialize_copy(c);
+    else { c->copy_pending = false; c->frames_from0++; }
     if (frame < 2) {                                                       // :150-154 (the destination is rewritten below)
         if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
         else do_memset(c, screen, n, kHole, n * 3);
@@ -803,22 +894,38 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     };
     // A pending in-place gap-filter write of the previous frame is dead now: this frame rewrites all of buffer 0.
     c->patch_target = nullptr;
-    // second stream: everything it does for this frame comes after what the main stream has done so far
-    CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
-    CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
-    if (overlap) {
-        // the tile rays depend on nothing of this frame: start them first, concurrently with the reprojection
+    // The previous frame's colorize + gap filter (third stream) read the slot this frame's tile rays and resolve pass
+    // write (exact mode; in ping-pong mode the slot of two frames ago, waiting is always safe and long satisfied).
+    auto join_fill = [&]() {
+        if (c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
+    };
+    bool tile_launched = false;
+    if (overlap && !from0) {
+        // the tile rays depend on nothing of this frame: start them first (second stream, behind what the main stream has
+        // done so far), concurrently with the reprojection
+        join_fill();
+        CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
+        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
         launch_tile(c->stream2);
         CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
+        tile_launched = true;
     }
-    {   // :177-198 source buffers in ascending offset = the reference's launch order
+    {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
         LAUNCH(c, "k_proj_scatter2");
-        const unsigned int nsrc = (unsigned int)src_count * n;
-        k_proj_scatter2<<<(nsrc + 255) / 256, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, (unsigned int)src_first * n, nsrc, pc);
+        const unsigned int nsrc = from0 ? n : (unsigned int)src_count * n;
+        k_proj_scatter2<<<(nsrc + 255) / 256, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
+                                                                  nsrc, from0 ? 2u * n : 0u, pc, from0 ? screen + 2 * (size_t)n : nullptr,
+                                                                  from0 ? reinterpret_cast<float4 *>(back) + 2 * (size_t)n : nullptr);
     }
-    // ping-pong: the previous frame's gap filter (second stream) reads the slot rendered into two frames ago... which is this
-    // frame's destination only every other frame; waiting here is always safe and long satisfied
-    if (pingpong && c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
+    join_fill();
+    if (overlap && !tile_launched) {
+        // the tile rays write buffer 0, which the pass above was still reading: they start beside the resolve pass
+        CU_CHECK(cudaEventRecord(c->ev_scatter_done, c->stream));
+        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_scatter_done, 0));
+        launch_tile(c->stream2);
+        CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
+        tile_launched = true;
+    }
     {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
         LAUNCH(c, "k_resolve_gather");
         GatherArgs ga = {screen, back, c->key, idb, fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc, next_resid_count};
@@ -831,28 +938,32 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (c->depth == 11) k_rays_holes<11><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
         else                k_rays_holes<14><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
     }
-    if (overlap) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
+    if (tile_launched) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
     else launch_tile(c->stream);
-    uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
     if (!pingpong || tex) {
-        // exact mode: the previous frame's gap filter (second stream) reads the cache copy this pass overwrites
-        if (!pingpong && c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
-        {   // :394-405 cache copy (target 2) + :429-437 colorize, one streaming pass
+        // exact mode, lazy: the copy stays pending (see above).  The gap filter goes to the third stream, behind this
+        // frame's rays; it reads the frame itself (buffer 0 == what buffer 2 will hold; the filter's in-place write is not
+        // issued inside the pipeline), so the colorized image is complete a few microseconds after the last ray.
+        if (!lazy && !pingpong) {   // SVO_NO_LAZY_COPY: :394-405 cache copy + :429-437 colorize now, on the main stream
             LAUNCH(c, "k_copy_colorize");
             k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
-                dscreen, reinterpret_cast<const float4 *>(dback), pingpong ? nullptr : screen + 2 * (size_t)n,
-                pingpong ? nullptr : reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
+                dscreen, reinterpret_cast<const float4 *>(dback), screen + 2 * (size_t)n, reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
         }
-        // :411-422 gap filter, second stream: reads the pre-filter image (exact: the cache copy just made, which the next
-        // frame only reads; ping-pong: the destination slot), writes the colorized image and the patch list
-        CU_CHECK(cudaEventRecord(c->ev_copy_done, c->stream));
-        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_copy_done, 0));
+        CU_CHECK(cudaEventRecord(c->ev_rays_done, c->stream));
+        if (lazy) {
+            c->copy_pending = true;
+            c->pend_src_s = dscreen; c->pend_src_b = dback; c->pend_dst_s = screen + 2 * (size_t)n; c->pend_dst_b = back + 2 * (size_t)n * 4;
+            c->pend_n = n; c->pend_res_x = res_x;
+        }
+        // :411-422 gap filter: reads the pre-filter frame (the destination slot: nothing writes it before the next frame's
+        // resolve pass, which waits for this), writes the colorized image and the patch image
+        CU_CHECK(cudaStreamWaitEvent(c->stream3, c->ev_rays_done, 0));
         {
-            LAUNCH_ON(c, "k_fill_list", c->stream2);
-            const SnapView view = {pingpong ? dscreen : screen + 2 * (size_t)n, dscreen, (int)n};
-            k_fill_list<<<c->num_sms * 2, 256, 0, c->stream2>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
+            LAUNCH_ON(c, "k_fill_list", c->stream3);
+            const SnapView view = {dscreen, dscreen, (int)n};
+            k_fill_list<<<c->num_sms * 2, 256, 0, c->stream3>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
         }
-        CU_CHECK(cudaEventRecord(c->ev_fill_done, c->stream2));
+        CU_CHECK(cudaEventRecord(c->ev_fill_done, c->stream3));
         c->fill_event_valid = true;
         c->fill_outstanding = true;
         c->patch_target = pingpong ? nullptr : dscreen;   // exact mode: buffer 0 still lacks the filtered words
@@ -865,6 +976,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
 }
 
 extern "C" int svo_frame_last_slot(void) { return g_ctx ? g_ctx->last_slot : 0; }
+extern "C" unsigned long long svo_frame_deferred_count(void) { return g_ctx ? g_ctx->frames_from0 : 0ull; }
 
 extern "C" int svo_frame_idbuf_size(void)
 {

@@ -265,18 +265,6 @@ __global__ void k_fillhole2(uint32_t *__restrict__ screen, const uint32_t *__res
 // ---------------------------------------------------------------------------------------------
 // raycast_colorize (kernel/kernel.cl:944-974)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t colorize_word(uint32_t word)
-{
-    const int a = (int)word;
-    const int t = a & 3;
-    const float i = (float)(a & (255 - 7));
-    const float tr = t == 0 ? 1.0f : t == 1 ? 1.0f : t == 2 ? 1.5f : 0.2f;       // color_tab :959-963
-    const float tg = t == 0 ? 1.0f : t == 1 ? 0.7f : t == 2 ? 0.8f : 0.8f;
-    const float tb = t == 0 ? 1.0f : t == 1 ? 0.3f : t == 2 ? 0.1f : 0.2f;
-    const int r = min(__float2int_rz(i * tr), 255), g = min(__float2int_rz(i * tg), 255), b = min(__float2int_rz(i * tb), 255);
-    return (uint32_t)(b + g * 256 + r * 65536);
-}
-
 __global__ void k_colorize(const uint32_t *__restrict__ screen, uint32_t *__restrict__ tex, int n)
 {
     const int stride = gridDim.x * blockDim.x;

@@ -71,6 +71,7 @@ _svo_launch_count = _sig("svo_launch_count", C.c_uint64)
 _svo_frame_fused = _sig("svo_frame_fused", None, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(FrameParams))
 _svo_frame_idbuf_size = _sig("svo_frame_idbuf_size", _i)
 _svo_frame_last_slot = _sig("svo_frame_last_slot", _i)
+_svo_frame_deferred_count = _sig("svo_frame_deferred_count", C.c_uint64)
 
 _svo_event_record = _sig("svo_event_record", None, _i)
 _svo_event_elapsed_ms = _sig("svo_event_elapsed_ms", C.c_float, _i, _i)
@@ -84,6 +85,7 @@ _svo_host_free = _sig("svo_host_free", None, _vp)
 _svo_copy_to_host_async = _sig("svo_copy_to_host_async", None, _vp, _vp, _sz, _sz)
 
 _svo_present_async = _sig("svo_present_async", None, _vp, _vp, _sz, _i)
+_svo_present_rgb24_async = _sig("svo_present_rgb24_async", None, _vp, _vp, _sz, _i)
 _svo_present_wait = _sig("svo_present_wait", None, _i)
 
 _raise_errors = False
@@ -252,6 +254,11 @@ def frame_last_slot():
     return int(_svo_frame_last_slot())
 
 
+def frame_deferred_count():
+    """Fused frames whose reprojection pass carried the previous frame's cache copy (see svo_frame_deferred_count)."""
+    return int(_svo_frame_deferred_count())
+
+
 def frame_idbuf_size():
     return int(_svo_frame_idbuf_size())
 
@@ -305,6 +312,11 @@ def host_alloc(nbytes):
     return (C.c_uint8 * nbytes).from_address(p)
 
 
+def host_free(buf):
+    """Release a buffer returned by host_alloc (the ctypes array must not be used afterwards)."""
+    _svo_host_free(C.addressof(buf))
+
+
 def copy_to_host_async(dst, src, size, srcofs=0):
     _svo_copy_to_host_async(C.addressof(dst), src.handle, size, srcofs)
     _check()
@@ -313,6 +325,12 @@ def copy_to_host_async(dst, src, size, srcofs=0):
 def present_async(dst, src, size, slot):
     """Frame read-back on the copy stream (overlaps the next frame); present_wait(slot) blocks until it has landed."""
     _svo_present_async(C.addressof(dst), src.handle, size, slot)
+    _check()
+
+
+def present_rgb24_async(dst, src, npixels, slot):
+    """present_async with the frame packed to R,G,B bytes on the device first (npixels*3 bytes land in dst)."""
+    _svo_present_rgb24_async(C.addressof(dst), src.handle, npixels, slot)
     _check()
 
 

@@ -241,17 +241,21 @@ def draw_prepared(p, sync=True):
         ocl.ocl_end_all_kernels()
 
 
-def draw_present(p, host_frames):
+def draw_present(p, host_frames, rgb24=False):
     """Pipelined headless frame: frame p.frame is rendered into colorize target (p.frame & 1) and its read-back into
     host_frames[p.frame & 1] (page-locked, ocl.host_alloc) is queued on the copy stream, so it overlaps the next frame.
-    The caller owns the image after ocl.present_wait(p.frame & 1)."""
+    The caller owns the image after ocl.present_wait(p.frame & 1).  rgb24: the frame arrives as R,G,B bytes (PPM payload,
+    3 bytes per pixel) instead of the PBO's 0x00RRGGBB words."""
     if S.mem_screenbuffer_tex2 is None:
         S.mem_screenbuffer_tex2 = ocl.ocl_malloc(S.mem_screenbuffer_tex.size)
     k = p.frame & 1
     tex = S.mem_screenbuffer_tex2 if k else S.mem_screenbuffer_tex
     S.frame = p.frame
     ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
-    ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 4, k)
+    if rgb24:
+        ocl.present_rgb24_async(host_frames[k], tex, p.res_x * p.res_y, k)
+    else:
+        ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 4, k)
     return k
 
 

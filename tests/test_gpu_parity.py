@@ -259,6 +259,93 @@ def test_frame_sequence_pingpong(svo, orc, world, res, nframes):
         svo.ocl_init(0)
 
 
+@pytest.mark.parametrize("res,nframes,observe", [((320, 192), 3, ()), ((320, 192), 7, ()), ((320, 192), 40, ()),
+                                                 ((320, 192), 12, (4, 5, 9)), ((200, 120), 9, ()),
+                                                 ((1920, 1024), 8, ()), ((1920, 1024), 7, (3,))])
+def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
+    """The schedule the bench runs: fused frames enqueued back to back with no observation in between, so every frame from
+    the third on reads the previous frame out of buffer 0 and carries its cache copy in the reprojection pass, while the
+    colorize pass and the gap filter run on the side stream (svo_frame_deferred_count proves it).  The colorized image of EVERY frame comes back through the
+    headless present path (no flush) and is compared with the oracle; after the last frame every buffer is compared.
+    `observe` lists frames after which the host reads the buffers (flushes the pipeline): the next frame must then fall
+    back to the cache copy as its source."""
+    octree, root = world
+    rx, ry = res
+    n = rx * ry
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4)
+    rc, ocl = svo.raycast, svo.ocl
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused")
+    host = [ocl.host_alloc(n * 4), ocl.host_alloc(n * 4)]
+    try:
+        tex_ref, params, obs_ref = [], [], {}
+        for f in range(nframes):
+            pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
+            O.draw(pos, rot)
+            tex_ref.append(O.tex.copy())
+            if f in observe:
+                obs_ref[f] = O.screen[:n].copy()
+            rc.set_camera(pos, rot)
+            params.append(rc.prepare_params(rx, ry, f))
+        base = ocl.frame_deferred_count()
+        expect_deferred = 0
+        for f in range(nframes):
+            if f >= 2:                                   # the caller owns host[f & 1] again: frame f-2 has landed
+                ocl.present_wait(f & 1)
+                got = np.frombuffer(host[f & 1], dtype=np.uint32).copy()
+                assert np.array_equal(got, tex_ref[f - 2]), f"frame {f - 2} tex"
+            k = rc.draw_present(params[f], host)
+            assert k == (f & 1)
+            if f >= 2 and (f - 1) not in observe:
+                expect_deferred += 1
+            if f in observe:
+                screen, back, idb = rc.read_buffers(rx, ry)      # flushes: buffer 0 gets the filter's in-place words
+                assert np.array_equal(screen[:n], obs_ref[f]), f"frame {f} colour (observed)"
+        for f in range(max(0, nframes - 2), nframes):
+            ocl.present_wait(f & 1)
+            got = np.frombuffer(host[f & 1], dtype=np.uint32).copy()
+            assert np.array_equal(got, tex_ref[f]), f"frame {f} tex"
+        assert ocl.frame_deferred_count() - base == (0 if os.environ.get("SVO_NO_LAZY_COPY") else expect_deferred)
+        screen, back, idb = rc.read_buffers(rx, ry)
+        assert rc.idbuf_size() == O.idbuf_size
+        assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), "ids"
+        assert np.array_equal(screen, O.screen[:4 * n]), "colour"
+        assert np.array_equal(back.view(np.uint32), O.back[:16 * n].view(np.uint32)), "xyz"
+    finally:
+        for h in host:
+            ocl.host_free(h)
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
+@pytest.mark.parametrize("res", [(320, 192), (201, 121)])
+def test_present_rgb24(svo, orc, world, res):
+    """Headless present as R,G,B bytes (svo_present_rgb24_async): the packed frame equals the 0x00RRGGBB image byte for
+    byte; 201x121 has a pixel count that is not a multiple of four (tail path of the pack kernel)."""
+    octree, root = world
+    rx, ry = res
+    n = rx * ry
+    rc, ocl = svo.raycast, svo.ocl
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused")
+    host = [ocl.host_alloc(n * 3), ocl.host_alloc(n * 3)]
+    try:
+        for f in range(4):
+            rc.set_camera((10 + 0.25 * f, 22, 9 + 0.2 * f), (0.4, 0.7 + 0.01 * f, 0.0))
+            k = rc.draw_present(rc.prepare_params(rx, ry, f), host, rgb24=True)
+            ocl.present_wait(k)
+            got = np.frombuffer(host[k], dtype=np.uint8).reshape(n, 3).copy()
+            tex = (svo.raycast.S.mem_screenbuffer_tex2 if k else svo.raycast.S.mem_screenbuffer_tex).to_numpy(np.uint32, n)
+            exp = np.stack([(tex >> 16) & 255, (tex >> 8) & 255, tex & 255], axis=1).astype(np.uint8)
+            assert np.array_equal(got, exp), f"frame {f}"
+            assert tex.max() < (1 << 24)
+    finally:
+        for h in host:
+            ocl.host_free(h)
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
 def test_golden_frames(svo):
     """The CUDA path against the committed vectors produced by the reference's own source (tests/golden)."""
     from golden.make_golden import golden_pose, NFRAMES
