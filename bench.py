@@ -180,49 +180,61 @@ def octree_words_per_ray(octree, root, frames=(0, 40)):
 
 
 def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, frames=48):
-    """BASELINE.json config 3: 3840x2160 on screen bands (stripes of --stripe-rows rows dealt round-robin to the ranks,
-    octree replicated): full raycasts (no exchange but the end-of-frame barrier and the colorized rows stored into rank
-    0's frame over NVLink) and the warped pipeline (reprojection by peer atomics).  Strong scaling: one image, all ranks."""
+    """BASELINE.json config 3: 3840x2160 on screen bands (stripes dealt round-robin to the ranks, octree replicated): full
+    raycasts (every ray stores its colorized pixel into rank 0's frame over NVLink; end-of-frame flag barrier off the
+    critical path) and the warped pipeline (reprojection by peer atomics).  Strong scaling: one image, all ranks.  The
+    stripe height is a layout parameter chosen per workload: fine stripes balance the full raycast (2160 rows do not
+    divide evenly into 64-row stripes over 8 ranks), coarse ones keep the warped pipeline's halo and id lists short."""
     RX, RY = 3840, 2160
     ocl, rc = svo.ocl, svo.raycast
-    db = svo.bands.DistributedBand(octree, root, RX, RY, local_rank, stripe_rows=args.stripe_rows, dist=dist)
 
     def params(f):
         rc.set_camera(*flythrough_pose(f))
         return rc.prepare_params(RX, RY, f)
 
-    def fence():
-        db.band.sync()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, items):
-        fence()
-        ocl.event_record(6)
-        for it in items:
-            fn(it)
-        ocl.event_record(7)
-        ms = ocl.event_elapsed_ms(6, 7)
-        fence()
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
-
     P = [params(f) for f in range(4 + frames)]
-    for p in P[:3]:
-        db.band.raycast(p)
-    ray_ms = timed(db.band.raycast, P[4:4 + frames])
-    for p in P[:4]:                                   # frames 0 and 1 are full raycasts through the hole path
-        db.band.frame(p)
-    warp_ms = timed(db.band.frame, P[4:4 + frames])
-    out = {"ranks": world, "stripe_rows": db.band.lay["SR"], "scaling": "strong", "frames": frames,
-           "full_raycast_mrays_per_s": frames * RX * RY / (ray_ms * 1e-3) / 1e6, "full_raycast_ms": ray_ms / frames,
-           "warped_fps": frames / (warp_ms * 1e-3), "warped_ms": warp_ms / frames,
-           "exchange": "peer atomicMin / peer gather / halo rows / colorized rows over NVLink, flag barriers in peer memory; no NCCL"}
-    db.close()
-    return out
+
+    def run(stripe_rows, what):
+        db = svo.bands.DistributedBand(octree, root, RX, RY, local_rank, stripe_rows=stripe_rows, dist=dist)
+
+        def fence():
+            db.band.sync()
+            if dist is not None:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        def timed(fn, items):
+            fence()
+            ocl.event_record(6)
+            for it in items:
+                fn(it)
+            db.band.join()                            # the last frame's barrier belongs to the timed region
+            ocl.event_record(7)
+            ms = ocl.event_elapsed_ms(6, 7)
+            fence()
+            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+
+        if what == "raycast":
+            for p in P[:3]:
+                db.band.raycast(p)
+            ms = timed(db.band.raycast, P[4:4 + frames])
+        else:
+            for p in P[:4]:                               # frames 0 and 1 are full raycasts through the hole path
+                db.band.frame(p)
+            ms = timed(db.band.frame, P[4:4 + frames])
+        sr = db.band.lay["SR"]
+        db.close()
+        return ms, sr
+
+    ray_ms, ray_sr = run(args.ray_stripe_rows, "raycast")
+    warp_ms, warp_sr = run(args.stripe_rows, "frame")
+    return {"ranks": world, "stripe_rows": warp_sr, "ray_stripe_rows": ray_sr, "scaling": "strong", "frames": frames,
+            "full_raycast_mrays_per_s": frames * RX * RY / (ray_ms * 1e-3) / 1e6, "full_raycast_ms": ray_ms / frames,
+            "warped_fps": frames / (warp_ms * 1e-3), "warped_ms": warp_ms / frames,
+            "exchange": "peer atomicMin / peer gather / halo rows / colorized pixels over NVLink, flag barriers in peer memory; no NCCL"}
 
 
 def builder_bench(svo, path, local_rank):
@@ -300,7 +312,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-frames", type=int, default=32)
     ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
+    ap.add_argument("--ray-stripe-rows", type=int, default=16, help="stripe height of the banded full raycast at 3840x2160")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (bands at 3840x2160, 64-camera batch, depth-14 terrain)")
+    ap.add_argument("--bands-only", action="store_true", help="only the 3840x2160 screen-band measurements (development aid)")
     ap.add_argument("--mode", default="fused", choices=["fused", "pingpong"],
                     help="fused: every buffer as the reference leaves it (cache copy kept); pingpong: SVO_FRAME_PINGPONG, no cache copy")
     args = ap.parse_args()
@@ -342,6 +356,14 @@ def main():
         dist.barrier()
     octree, root, stats = svo.scene.octree_init(path)          # .rle4 loader -> direct compact-octree builder
     rc, ocl = svo.raycast, svo.ocl
+    if args.bands_only:
+        rc.S.mode = args.mode                                     # prepare_params() without raycast_init()
+        out = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args)
+        if rank == 0:
+            print(json.dumps({"bands_3840x2160": out}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     rc.raycast_init(octree, root, max_w=RES_X, max_h=RES_Y, device=local_rank, mode=args.mode)
     n = RES_X * RES_Y
 
@@ -387,17 +409,19 @@ def main():
     rc.reset_frames()
     for f in range(args.warmup):
         rc.draw_prepared(P[f], sync=True)
-    host_frames = [ocl.host_alloc(n * 4), ocl.host_alloc(n * 4)]
+    DEPTH = 3                                                        # frames in flight: render f, pack f-1, copy f-2
+    host_frames = [ocl.host_alloc(n * 3) for _ in range(DEPTH)]
     sync_all()
     t0 = time.perf_counter()
     for f in range(args.warmup, total):
         # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame as R,G,B
-        # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frame renders.  The
-        # caller owns frame f-1 after present_wait.
+        # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frames render.  The
+        # caller owns frame f-2 after its present_wait.
         k = rc.draw_present(P[f], host_frames, rgb24=True)
-        if f > args.warmup:
-            ocl.present_wait(k ^ 1)
-    ocl.present_wait(k)
+        if f - (DEPTH - 1) >= args.warmup:
+            ocl.present_wait((f - (DEPTH - 1)) % DEPTH)
+    for f in range(max(args.warmup, total - (DEPTH - 1)), total):
+        ocl.present_wait(f % DEPTH)
     e2e_s = time.perf_counter() - t0
     host_frame = host_frames[k]
     sampler.stop_flag = True

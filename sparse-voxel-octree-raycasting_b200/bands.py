@@ -34,6 +34,7 @@ _band_connect_local = ocl._sig("svo_band_connect_local", None, _vp, C.POINTER(_v
 _band_frame = ocl._sig("svo_band_frame", None, _vp, C.POINTER(ocl.FrameParams))
 _band_raycast = ocl._sig("svo_band_raycast", None, _vp, C.POINTER(ocl.FrameParams))
 _band_sync = ocl._sig("svo_band_sync", None, _vp)
+_band_join = ocl._sig("svo_band_join", None, _vp)
 _band_read = ocl._sig("svo_band_read", _i, _vp, _i, _vp, _sz, _sz)
 _band_write = ocl._sig("svo_band_write", _i, _vp, _i, _vp, _sz, _sz)
 _band_ctx = ocl._sig("svo_band_ctx", _vp, _vp)
@@ -112,6 +113,11 @@ class Band:
 
     def sync(self):
         _band_sync(self.handle)
+        ocl._check()
+
+    def join(self):
+        """Order the stream behind the end-of-frame barrier of the last raycast() (svo_band_join)."""
+        _band_join(self.handle)
         ocl._check()
 
     def last_slot(self):

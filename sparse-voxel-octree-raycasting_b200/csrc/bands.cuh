@@ -316,13 +316,13 @@ k_band_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
     }
 }
 
 // rays for the owned rows of the rectangle [x0, x0+gx) x [y0, y0+gy) clipped to the screen, 8x4 footprints per warp:
 // the tile refresh (raycast_fine_2, kernel.cl:846-942) and, with the whole screen as the rectangle, a banded full raycast
-template <int D>
+template <int D, bool STRAIGHT>      // STRAIGHT: the sparse tile refresh; false: a full-screen raycast (ray.cuh, fetch_child)
 __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
                  BandMap m, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs)
@@ -339,7 +339,7 @@ k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const 
         if (lx >= gx || lr >= lrows) continue;
         const int idx = lx + add_x, idy = m.global_row(lr);
         if (idy < add_y || idy >= add_y + gy || idx >= m.res_x || idy >= m.res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        trace_pixel<D, kRaysBlock, STRAIGHT>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 

@@ -384,7 +384,7 @@ k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 
@@ -403,7 +403,7 @@ k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint3
         if (lx >= gx || ly >= gy) continue;
         const int idx = lx + add_x, idy = ly + add_y;
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
 }
 

@@ -87,6 +87,7 @@ def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth
     S.mem_screenbuffer = ocl.ocl_malloc(size * 4 * 4)                              # :85
     S.mem_screenbuffer_tex = ocl.ocl_malloc(size * 4)                              # PBO stand-in (:88-89)
     S.mem_screenbuffer_tex2 = None                                                 # second colorize target (draw_present)
+    S.present_tex = []                                                             # colorize targets of the frames in flight
     S.mem_x = S.mem_y = None                                                       # dead kernel arguments (:170-171)
     S.mem_z = ocl.ocl_malloc(4 * size)                                             # :172 (only ever memset)
     # :268-270 allocates MAXPIX + MAXB words, but counts + offsets + ids need N + 2B: the reference overruns by B words
@@ -242,14 +243,17 @@ def draw_prepared(p, sync=True):
 
 
 def draw_present(p, host_frames, rgb24=False):
-    """Pipelined headless frame: frame p.frame is rendered into colorize target (p.frame & 1) and its read-back into
-    host_frames[p.frame & 1] (page-locked, ocl.host_alloc) is queued on the copy stream, so it overlaps the next frame.
-    The caller owns the image after ocl.present_wait(p.frame & 1).  rgb24: the frame arrives as R,G,B bytes (PPM payload,
-    3 bytes per pixel) instead of the PBO's 0x00RRGGBB words."""
-    if S.mem_screenbuffer_tex2 is None:
-        S.mem_screenbuffer_tex2 = ocl.ocl_malloc(S.mem_screenbuffer_tex.size)
-    k = p.frame & 1
-    tex = S.mem_screenbuffer_tex2 if k else S.mem_screenbuffer_tex
+    """Pipelined headless frame: with D = len(host_frames) (2..4) buffers, frame p.frame is rendered into colorize target
+    k = p.frame % D and its read-back into host_frames[k] (page-locked, ocl.host_alloc) is queued on the copy stream, so
+    it overlaps the following frames.  The caller owns the image after ocl.present_wait(k) and must have consumed it
+    before frame p.frame + D is issued.  rgb24: the frame arrives as R,G,B bytes (PPM payload, 3 bytes per pixel) instead
+    of the PBO's 0x00RRGGBB words."""
+    depth = len(host_frames)
+    while len(S.present_tex) < depth:                    # one colorize target per frame in flight
+        S.present_tex.append(S.mem_screenbuffer_tex if not S.present_tex else ocl.ocl_malloc(S.mem_screenbuffer_tex.size))
+    S.mem_screenbuffer_tex2 = S.present_tex[1] if depth > 1 else None
+    k = p.frame % depth
+    tex = S.present_tex[k]
     S.frame = p.frame
     ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
     if rgb24:
@@ -336,7 +340,10 @@ def raycast_exit():
     """src/raycast.h:511-517."""
     if not S.ready:
         return
-    for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_screenbuffer_tex2", "mem_z", "mem_idbuffer"):
+    for m in getattr(S, "present_tex", [])[1:]:
+        m.free()
+    S.present_tex, S.mem_screenbuffer_tex2 = [], None
+    for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_z", "mem_idbuffer"):
         m = getattr(S, name, None)
         if m is not None:
             m.free()
