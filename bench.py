@@ -241,7 +241,9 @@ def builder_bench(svo, path, local_rank):
     """the compact octree of the bench scene built by the host builder and by the device builder
     (svo_octree_build_device: the node pool is built on the GPU and stays there); the two arrays must be identical."""
     ocl = svo.ocl
+    t0 = time.perf_counter()
     vox = svo.scene.rle4_load(path)
+    load_s = time.perf_counter() - t0
     x, y, z, c = vox.arrays()
     vox.free()
     t0 = time.perf_counter()
@@ -254,9 +256,17 @@ def builder_bench(svo, path, local_rank):
     dev_s = time.perf_counter() - t0
     same = bool(droot == root and mem.size == words.nbytes and np.array_equal(mem.to_numpy(), words))
     mem.free()
+    # file -> device octree, the slab stream decoded on the GPU (no host voxel stream at all)
+    t0 = time.perf_counter()
+    mem, droot2, _ = svo.scene.octree_init_device(path, depth=11)
+    file_dev_s = time.perf_counter() - t0
+    same2 = bool(droot2 == root and mem.size == words.nbytes and np.array_equal(mem.to_numpy(), words))
+    mem.free()
     ocl.ocl_exit()
-    return {"voxels": int(len(x)), "host_builder_s": round(host_s, 3), "device_builder_s": round(dev_s, 3),
-            "identical": same, "host_threads": os.cpu_count(), "includes": "device: H2D of the voxel stream (16 B/voxel) + sort + emit + normal nodes"}
+    return {"voxels": int(len(x)), "host_rle4_load_s": round(load_s, 3), "host_builder_s": round(host_s, 3), "device_builder_s": round(dev_s, 3),
+            "file_to_device_octree_s": round(file_dev_s, 3), "identical": same and same2, "host_threads": os.cpu_count(),
+            "includes": "device_builder: H2D of the voxel stream (16 B/voxel) + sort + emit + normal nodes; file_to_device_octree: file read + "
+                        "column walk on the host, slab decode + the same builder on the GPU (compare with host_rle4_load_s + host_builder_s)"}
 
 
 def terrain14_bench(svo, args, frames=64):
@@ -411,6 +421,14 @@ def main():
         rc.draw_prepared(P[f], sync=True)
     DEPTH = 3                                                        # frames in flight: render f, pack f-1, copy f-2
     host_frames = [ocl.host_alloc(n * 3) for _ in range(DEPTH)]
+    # PCIe warm-up: the link idles at a low speed and takes tens of ms of traffic to train up; a timed loop that starts cold
+    # measured 1 700-2 000 frames/s in one run out of five.  64 untimed read-backs of the last warm-up frame.
+    for i in range(64):
+        ocl.present_rgb24_async(host_frames[i % DEPTH], rc.S.mem_screenbuffer_tex, n, i % DEPTH)
+        if i >= DEPTH - 1:
+            ocl.present_wait((i - (DEPTH - 1)) % DEPTH)
+    for i in range(64 - (DEPTH - 1), 64):
+        ocl.present_wait(i % DEPTH)
     sync_all()
     t0 = time.perf_counter()
     for f in range(args.warmup, total):

@@ -51,6 +51,15 @@ void            svo_voxels_free(svo_voxels_t v);
 /* RLE4::load(filename, palette, addx, addy, addz): mip 0 of the file as a voxel stream in the loader's
  * set_voxel order (slice, x, y1 ascending).  NULL + message on stderr if the file cannot be read. */
 svo_voxels_t    svo_rle4_load(const char *path, int palette, int addx, int addy, int addz);
+/* The same for mip volume `mip` of the file (0 <= mip < nummaps; the maps are stored back to back, Rle4.cpp:26-43).  The
+ * reference reads every map and voxelises only the first (`loopi(0,1)//nummaps`, :91). */
+svo_voxels_t    svo_rle4_load_mip(const char *path, int mip, int palette, int addx, int addy, int addz);
+/* .rle4 -> device-resident octree without a host voxel stream: the host reads the file and walks
+ * the column headers (Rle4.cpp:55-77), the slabs are decoded on the device of the current context (one thread per
+ * column) straight into the builder of svo_octree_build_device.  Same voxels, order and colours as svo_rle4_load_mip +
+ * svo_octree_build, word for word.  *num_voxels_out = voxels decoded (duplicates included). */
+svo_mem_t       svo_octree_load_rle4_device(const char *path, int mip, int palette, int addx, int addy, int addz, int depth,
+                                            uint32_t *root_out, uint64_t *num_voxels_out, uint64_t *num_unique_out);
 /* Inverse (fixture / stand-in scenes): writes a 1-mip .rle4 of size sx*sy*sz holding the stream's voxels.
  * Colours are stored as the 16-bit value t with (t & 255) = 255 - (rgba.x - 1), bits 5.. = rgba.y>>3, bits 10.. =
  * rgba.z>>3 (consistent only where those overlap; the stand-in scenes use rgba.y = rgba.z = derived values). 0 = ok. */

@@ -191,33 +191,37 @@ __global__ void k_blocks(Vox v, const uint32_t *__restrict__ block_lo, uint32_t 
 }
 
 // ---- host: the "normal" nodes (tree depths 0..D-7) from the block table (convert_tree_blocks, octree.h:232-293) ----
-struct BlockInfo { uint32_t prefix, base, mask, minidx; };
-struct Ret { uint32_t ptr, minidx; };
+struct BlockInfo { uint32_t prefix, base, mask, minidx, mincol; };   // mincol = colour of voxel minidx (first inserted in the block)
+struct Ret { uint32_t ptr, minidx, mincol; };
 struct NormalEmitter {
-    const std::vector<BlockInfo> &blk; const uint32_t *rgba; int D;
+    const std::vector<BlockInfo> &blk; int D;
     std::vector<uint32_t> out;
     uint32_t ofs = 0;
     Ret node(size_t lo, size_t hi, int d)
     {
         const int shift = 3 * (D - 7 - d);                    // block prefixes carry 3 bits per depth 0 .. D-7
-        uint32_t child[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mask = 0, minidx = 0xffffffffu;
+        uint32_t child[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mask = 0, minidx = 0xffffffffu, mincol = 0;
         size_t cur = lo;
         for (uint32_t c = 0; c < 8; ++c) {
             size_t e = cur;
             while (e < hi && ((blk[e].prefix >> shift) & 7u) == c) ++e;
             if (e > cur) {
                 mask |= 1u << c;
-                if (d < D - 7) { const Ret r = node(cur, e, d + 1); child[c] = r.ptr; minidx = std::min(minidx, r.minidx); }
-                else { const BlockInfo &b = blk[cur]; child[c] = ((b.base >> 6) << 9) | (1u << 8) | b.mask; minidx = std::min(minidx, b.minidx); }   // :265
+                if (d < D - 7) { const Ret r = node(cur, e, d + 1); child[c] = r.ptr; if (r.minidx < minidx) { minidx = r.minidx; mincol = r.mincol; } }
+                else {
+                    const BlockInfo &b = blk[cur];
+                    child[c] = ((b.base >> 6) << 9) | (1u << 8) | b.mask;                                                            // :265
+                    if (b.minidx < minidx) { minidx = b.minidx; mincol = b.mincol; }
+                }
             }
             cur = e;
         }
-        const uint32_t col = d == 0 ? 0u : rgba[minidx];      // the pre-pushed root never gets a colour (src/raycast.h:15-17)
+        const uint32_t col = d == 0 ? 0u : mincol;            // the pre-pushed root never gets a colour (src/raycast.h:15-17)
         if (out.size() < ofs + 10) out.resize(ofs + 10, 0u);
         for (int j = 0; j < 8; ++j) out[ofs + j] = child[j];
         out[ofs + 8] = col; out[ofs + 9] = col;               // :280-281
         ofs += 10;
-        return Ret{((ofs - 10) << 9) | mask, minidx};         // :292
+        return Ret{((ofs - 10) << 9) | mask, minidx, mincol}; // :292
     }
 };
 
@@ -226,19 +230,16 @@ T *dalloc(size_t n) { T *p = nullptr; CU_CHECK(cudaMalloc(&p, (n ? n : 1) * size
 
 }  // namespace
 
-extern "C" svo_mem_t svo_octree_build_device(size_t n, const uint32_t *x, const uint32_t *y, const uint32_t *z, const uint32_t *rgba,
-                                             int depth, uint32_t *root_out, uint64_t *num_unique_out)
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t *__restrict__ dst, uint32_t n)
 {
-    svo_ctx_t ctx = svo_ctx_get_current();
-    if (!ctx) { svo_fail(-100, "svo_octree_build_device: no context (svo_init first)"); return nullptr; }
-    if (depth < 8 || depth > 15 || n == 0 || n >= 0xffffffffull || !x || !y || !z || !rgba) { svo_fail(-130, "svo_octree_build_device: bad arguments"); return nullptr; }
-    cudaStream_t st = (cudaStream_t)svo_ctx_stream(ctx);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+// steps 1-8 on a voxel stream that already lies in device memory; takes ownership of (frees) the four arrays
+static svo_mem_t build_from_device(cudaStream_t st, size_t n, uint32_t *dx, uint32_t *dy, uint32_t *dz, uint32_t *drgba, int depth,
+                                   uint32_t *root_out, uint64_t *num_unique_out)
+{
     const int grid = 148 * 8;
-    uint32_t *dx = dalloc<uint32_t>(n), *dy = dalloc<uint32_t>(n), *dz = dalloc<uint32_t>(n), *drgba = dalloc<uint32_t>(n);
-    CU_CHECK(cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemcpyAsync(dz, z, n * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemcpyAsync(drgba, rgba, n * 4, cudaMemcpyHostToDevice, st));
     unsigned long long *key = dalloc<unsigned long long>(n), *key2 = dalloc<unsigned long long>(n);
     uint32_t *idx = dalloc<uint32_t>(n), *idx2 = dalloc<uint32_t>(n);
     k_make_keys<<<grid, 256, 0, st>>>(dx, dy, dz, key, idx, n, (1u << depth) - 1u);
@@ -282,11 +283,12 @@ extern "C" svo_mem_t svo_octree_build_device(size_t n, const uint32_t *x, const 
     CU_CHECK(cudaFree(key)); CU_CHECK(cudaFree(idx));
     // 5.-7. sizes, bases, records
     uint32_t *words = dalloc<uint32_t>(nblocks + 1), *mask = dalloc<uint32_t>(nblocks), *minidx = dalloc<uint32_t>(nblocks);
-    uint32_t *prefix = dalloc<uint32_t>(nblocks);
+    uint32_t *prefix = dalloc<uint32_t>(nblocks), *mincol = dalloc<uint32_t>(nblocks);
     unsigned long long *base = dalloc<unsigned long long>(nblocks + 1);
     const Vox v = {ukey, first_idx, leaf_col, drgba, depth};
     const int bgrid = (int)((nblocks + 63) / 64);
     k_blocks<false><<<bgrid, 64, 0, st>>>(v, head, nblocks, nu, words, mask, minidx, prefix, nullptr, nullptr);
+    k_gather_u32<<<grid, 256, 0, st>>>(drgba, minidx, mincol, nblocks);       // colour of the first voxel inserted in each block
     {
         size_t tmp_bytes = 0;
         CU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, words, base, (int)nblocks, st));
@@ -308,25 +310,165 @@ extern "C" svo_mem_t svo_octree_build_device(size_t n, const uint32_t *x, const 
     // 8. normal nodes on the host
     std::vector<BlockInfo> blk(nblocks);
     {
-        std::vector<uint32_t> h_prefix(nblocks), h_mask(nblocks), h_min(nblocks);
+        std::vector<uint32_t> h_prefix(nblocks), h_mask(nblocks), h_min(nblocks), h_col(nblocks);
         std::vector<unsigned long long> h_base(nblocks);
         CU_CHECK(cudaMemcpyAsync(h_prefix.data(), prefix, nblocks * 4ull, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaMemcpyAsync(h_mask.data(), mask, nblocks * 4ull, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaMemcpyAsync(h_min.data(), minidx, nblocks * 4ull, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemcpyAsync(h_col.data(), mincol, nblocks * 4ull, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaMemcpyAsync(h_base.data(), base, nblocks * 8ull, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaStreamSynchronize(st));
         for (uint32_t b = 0; b < nblocks; ++b)
-            blk[b] = BlockInfo{h_prefix[b], (uint32_t)(kNormalWords + h_base[b]), h_mask[b], h_min[b]};
+            blk[b] = BlockInfo{h_prefix[b], (uint32_t)(kNormalWords + h_base[b]), h_mask[b], h_min[b], h_col[b]};
     }
-    NormalEmitter ne{blk, rgba, depth};
+    NormalEmitter ne{blk, depth};
     const Ret root = ne.node(0, blk.size(), 0);
     if (ne.ofs > kNormalWords) { svo_fail(-132, "svo_octree_build_device: more normal nodes than the reserved region holds"); return nullptr; }
     CU_CHECK(cudaMemcpyAsync(out, ne.out.data(), (size_t)ne.ofs * 4, cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaStreamSynchronize(st));
     for (void *p : {(void *)drgba, (void *)flag, (void *)head, (void *)d_count, (void *)ukey, (void *)first_idx, (void *)leaf_col,
-                    (void *)words, (void *)mask, (void *)minidx, (void *)prefix, (void *)base})
+                    (void *)words, (void *)mask, (void *)minidx, (void *)prefix, (void *)mincol, (void *)base})
         CU_CHECK(cudaFree(p));
     if (root_out) *root_out = root.ptr;
     if (num_unique_out) *num_unique_out = nu;
     return m;
+}
+
+extern "C" svo_mem_t svo_octree_build_device(size_t n, const uint32_t *x, const uint32_t *y, const uint32_t *z, const uint32_t *rgba,
+                                             int depth, uint32_t *root_out, uint64_t *num_unique_out)
+{
+    svo_ctx_t ctx = svo_ctx_get_current();
+    if (!ctx) { svo_fail(-100, "svo_octree_build_device: no context (svo_init first)"); return nullptr; }
+    if (depth < 8 || depth > 15 || n == 0 || n >= 0xffffffffull || !x || !y || !z || !rgba) { svo_fail(-130, "svo_octree_build_device: bad arguments"); return nullptr; }
+    cudaStream_t st = (cudaStream_t)svo_ctx_stream(ctx);
+    uint32_t *dx = dalloc<uint32_t>(n), *dy = dalloc<uint32_t>(n), *dz = dalloc<uint32_t>(n), *drgba = dalloc<uint32_t>(n);
+    CU_CHECK(cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(dz, z, n * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(drgba, rgba, n * 4, cudaMemcpyHostToDevice, st));
+    return build_from_device(st, n, dx, dy, dz, drgba, depth, root_out, num_unique_out);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// .rle4 -> device octree without a host voxel stream.  The host only reads the file and walks the
+// column headers (the reference's own offset walk, src/octree/Rle4.cpp:55-77: a column's length is stored at its start, so
+// the offsets are a linked list); the slabs are decoded on the device, one thread per column, straight into the voxel
+// stream the builder above consumes -- same voxels, same insertion order (slice, x, y1 ascending, Rle4.cpp:95-123), same
+// colours (:125-151) as svo_rle4_load, 2-4 bytes per voxel over PCIe instead of 16.  `mip` selects which of the file's
+// mip volumes is voxelised (the reference: always 0, `loopi(0,1)//nummaps`, :91).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Rle4Dev {
+    const uint16_t *slabs; const uint32_t *colofs;
+    uint32_t ncols; int sx, sy; int palette, addx, addy, addz;
+};
+
+__device__ __forceinline__ uint32_t rle4_colour_dev(uint32_t tcol, int palette)      // Rle4.cpp:125-151 (host: scene_io.cpp)
+{
+    const uint32_t color = (tcol >> 8) & 3u, lo = tcol & 255u;
+    uint32_t intensity = (lo * lo) / 255u;                                          // float of an int quotient, clamped: stays integral
+    if (intensity < 2u) intensity = 2u;
+    if (intensity > 255u) intensity = 255u;
+    uint32_t cx = (color + ((intensity >> 3) << 3)) & 255u;
+    const uint32_t cy = ((tcol >> 5) << 3) & 255u, cz = ((tcol >> 10) << 3) & 255u;
+    if (!palette) cx = (1u + ((255u - lo) & 0xfcu)) & 255u;
+    return cx | (cy << 8) | (cz << 16);
+}
+
+template <bool EMIT>
+__global__ void k_rle4_columns(Rle4Dev d, uint32_t *__restrict__ count, const uint32_t *__restrict__ base,
+                               uint32_t *__restrict__ x, uint32_t *__restrict__ y, uint32_t *__restrict__ z, uint32_t *__restrict__ rgba)
+{
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= d.ncols) return;
+    const uint32_t ofs = d.colofs[col];
+    const uint32_t cnt = d.slabs[ofs], numtex = d.slabs[ofs + 1];
+    const uint16_t *p = d.slabs + ofs + 2, *pt = p + cnt, *pend = pt + numtex;
+    const uint32_t vx = (uint32_t)((int)(col % (uint32_t)d.sx) + d.addx), vz = (uint32_t)((int)(col / (uint32_t)d.sx) + d.addz);
+    uint32_t y1 = 0, nv = 0;
+    const uint32_t out = EMIT ? base[col] : 0u;
+    for (uint32_t s = 0; s < cnt; ++s) {
+        const uint32_t sl = p[s];
+        y1 += sl & 1023u;
+        const uint32_t y2 = y1 + (sl >> 10);
+        for (; y1 < y2; ++y1, ++pt)
+            if (y1 < (uint32_t)d.sy && pt < pend) {
+                if (EMIT) {
+                    const uint32_t o = out + nv;
+                    x[o] = vx; y[o] = (uint32_t)(d.sy - 1 - (int)y1 + d.addy); z[o] = vz; rgba[o] = rle4_colour_dev(*pt, d.palette);
+                }
+                ++nv;
+            }
+    }
+    if (!EMIT) count[col] = nv;
+}
+
+}  // namespace
+
+extern "C" svo_mem_t svo_octree_load_rle4_device(const char *path, int mip, int palette, int addx, int addy, int addz, int depth,
+                                                 uint32_t *root_out, uint64_t *num_voxels_out, uint64_t *num_unique_out)
+{
+    svo_ctx_t ctx = svo_ctx_get_current();
+    if (!ctx) { svo_fail(-100, "svo_octree_load_rle4_device: no context (svo_init first)"); return nullptr; }
+    if (!path || mip < 0 || mip >= 16 || depth < 8 || depth > 15) { svo_fail(-133, "svo_octree_load_rle4_device: bad arguments"); return nullptr; }
+    FILE *f = fopen(path, "rb");
+    if (!f) { svo_fail(-134, "File not found: %s", path); return nullptr; }
+    int32_t nummaps = 0, hdr[4] = {0, 0, 0, 0};
+    std::vector<uint16_t> slabs;
+    bool ok = fread(&nummaps, 4, 1, f) == 1 && nummaps > 0 && nummaps <= 16 && mip < nummaps;
+    for (int m = 0; ok && m <= mip; ++m) {                                          // maps are stored back to back (Rle4.cpp:26-43)
+        ok = fread(hdr, 4, 4, f) == 4 && hdr[0] > 0 && hdr[1] > 0 && hdr[2] > 0 && hdr[3] > 0;
+        if (ok && m < mip) ok = fseek(f, (long)hdr[3] * 2, SEEK_CUR) == 0;
+    }
+    if (ok) {
+        slabs.resize((size_t)hdr[3] + 4, 0);
+        ok = fread(slabs.data(), 2, (size_t)hdr[3], f) == (size_t)hdr[3];
+    }
+    fclose(f);
+    if (!ok) { svo_fail(-135, "%s: not a readable .rle4 file (or no mip %d)", path, mip); return nullptr; }
+    const int sx = hdr[0], sy = hdr[1], sz = hdr[2];
+    // column offsets; a truncated stream ends the scene at the last complete column (as svo_rle4_load does)
+    std::vector<uint32_t> colofs;
+    colofs.reserve((size_t)sx * sz);
+    size_t ofs = 0;
+    for (size_t c = 0; c < (size_t)sx * sz; ++c) {
+        if (ofs + 2 > (size_t)hdr[3]) break;
+        const size_t len = (size_t)slabs[ofs] + slabs[ofs + 1] + 2;
+        if (ofs + len > (size_t)hdr[3]) break;
+        colofs.push_back((uint32_t)ofs);
+        ofs += len;
+    }
+    const uint32_t ncols = (uint32_t)colofs.size();
+    if (!ncols) { svo_fail(-136, "%s: no voxel columns", path); return nullptr; }
+    cudaStream_t st = (cudaStream_t)svo_ctx_stream(ctx);
+    uint16_t *dslabs = dalloc<uint16_t>(slabs.size());
+    uint32_t *dcolofs = dalloc<uint32_t>(ncols), *dcount = dalloc<uint32_t>(ncols + 1), *dbase = dalloc<uint32_t>(ncols + 1);
+    CU_CHECK(cudaMemcpyAsync(dslabs, slabs.data(), slabs.size() * 2, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(dcolofs, colofs.data(), (size_t)ncols * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemsetAsync(dcount + ncols, 0, 4, st));
+    const Rle4Dev d = {dslabs, dcolofs, ncols, sx, sy, palette, addx, addy, addz};
+    const int cgrid = (int)((ncols + 127) / 128);
+    k_rle4_columns<false><<<cgrid, 128, 0, st>>>(d, dcount, nullptr, nullptr, nullptr, nullptr, nullptr);
+    {
+        size_t tmp_bytes = 0;
+        CU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, dcount, dbase, (int)ncols + 1, st));
+        void *tmp = dalloc<unsigned char>(tmp_bytes);
+        CU_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, dcount, dbase, (int)ncols + 1, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        CU_CHECK(cudaFree(tmp));
+    }
+    uint32_t n = 0;                                                                  // <= the slab count, which is an int32
+    CU_CHECK(cudaMemcpy(&n, dbase + ncols, 4, cudaMemcpyDeviceToHost));
+    if (num_voxels_out) *num_voxels_out = n;
+    if (!n) {
+        for (void *p : {(void *)dslabs, (void *)dcolofs, (void *)dcount, (void *)dbase}) CU_CHECK(cudaFree(p));
+        svo_fail(-136, "%s: no voxels", path);
+        return nullptr;
+    }
+    uint32_t *dx = dalloc<uint32_t>(n), *dy = dalloc<uint32_t>(n), *dz = dalloc<uint32_t>(n), *drgba = dalloc<uint32_t>(n);
+    k_rle4_columns<true><<<cgrid, 128, 0, st>>>(d, nullptr, dbase, dx, dy, dz, drgba);
+    CU_CHECK(cudaStreamSynchronize(st));
+    for (void *p : {(void *)dslabs, (void *)dcolofs, (void *)dcount, (void *)dbase}) CU_CHECK(cudaFree(p));
+    return build_from_device(st, n, dx, dy, dz, drgba, depth, root_out, num_unique_out);
 }

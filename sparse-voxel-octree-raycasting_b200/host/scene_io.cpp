@@ -44,11 +44,20 @@ static inline uint32_t rle4_colour(uint16_t tcol, int palette)
 // slab = skip:10 | run:6.  Only map 0 is voxelised (:91); voxel = (x, sy-1-y1, slice) (:145,160).
 extern "C" svo_voxels_t svo_rle4_load(const char *path, int palette, int addx, int addy, int addz)
 {
+    return svo_rle4_load_mip(path, 0, palette, addx, addy, addz);
+}
+
+extern "C" svo_voxels_t svo_rle4_load_mip(const char *path, int mip, int palette, int addx, int addy, int addz)
+{
     FILE *f = fopen(path, "rb");
     if (!f) { fprintf(stderr, "svo_b200: File not found: %s\n", path); return nullptr; }
     int32_t nummaps = 0, hdr[4] = {0, 0, 0, 0};
     std::vector<uint16_t> slabs;
-    bool ok = fread(&nummaps, 4, 1, f) == 1 && nummaps > 0 && nummaps <= 16 && fread(hdr, 4, 4, f) == 4 && hdr[3] > 0;
+    bool ok = fread(&nummaps, 4, 1, f) == 1 && nummaps > 0 && nummaps <= 16 && mip >= 0 && mip < nummaps;
+    for (int m = 0; ok && m <= mip; ++m) {                      // the mip volumes are stored back to back (Rle4.cpp:26-43)
+        ok = fread(hdr, 4, 4, f) == 4 && hdr[3] > 0;
+        if (ok && m < mip) ok = fseek(f, (long)hdr[3] * 2, SEEK_CUR) == 0;
+    }
     if (ok) {
         slabs.resize((size_t)hdr[3] + 4, 0);
         ok = fread(slabs.data(), 2, (size_t)hdr[3], f) == (size_t)hdr[3];

@@ -101,8 +101,28 @@ def build_octree_device(x, y, z, rgba, depth=11):
     return ocl.Mem(h, int(ocl._svo_mem_size(h))), int(root.value), dict(num_voxels=len(x), num_unique=int(nu.value))
 
 
-def rle4_load(path, palette=0, addx=0, addy=0, addz=0):
-    return Voxels(_rle4_load(os.fsencode(path), palette, addx, addy, addz))
+_rle4_load_mip = _sig("svo_rle4_load_mip", _vp, C.c_char_p, _i, _i, _i, _i, _i)
+_load_rle4_device = _sig("svo_octree_load_rle4_device", _vp, C.c_char_p, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_uint32),
+                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+
+
+def rle4_load(path, palette=0, addx=0, addy=0, addz=0, mip=0):
+    h = _rle4_load_mip(os.fsencode(path), mip, palette, addx, addy, addz)
+    if not h:
+        raise RuntimeError(f"svo_b200: cannot load mip {mip} of {path}")
+    return Voxels(h)
+
+
+def octree_init_device(path, depth=11, mip=0, palette=0, addx=0, addy=0, addz=0):
+    """octree_init() with the .rle4 decoded and the octree built on the GPU of the current context (ocl_init first):
+    -> (Mem usable as mem_octree, octree_root_normal, stats).  Nothing but the file's slab stream crosses PCIe."""
+    from . import ocl
+    root, nv, nu = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    h = _load_rle4_device(os.fsencode(path), mip, palette, addx, addy, addz, depth, C.byref(root), C.byref(nv), C.byref(nu))
+    ocl._check()
+    if not h:
+        raise RuntimeError("svo_octree_load_rle4_device failed")
+    return ocl.Mem(h, int(ocl._svo_mem_size(h))), int(root.value), dict(num_voxels=int(nv.value), num_unique=int(nu.value))
 
 
 def octree_init(path, depth=11):

@@ -559,3 +559,55 @@ def test_device_octree_builder(svo, orc, name, depth):
         assert st["num_unique"] <= len(sc[0])
     finally:
         mem.free()
+
+
+@pytest.mark.parametrize("case", ["s1", "terrain_offsets_palette", "mip1", "truncated"])
+def test_device_rle4_decode(svo, orc, tmp_path, case):
+    """svo_octree_load_rle4_device: the .rle4 slab stream decoded on the GPU and fed to the device
+    builder gives, word for word, the octree of the host loader + host builder (which the CPU tests pin against the
+    reference's RLE4::load + convert_tree_blocks) -- with offsets and the palette colour mapping, for a higher mip volume
+    of a multi-mip file, and for a stream cut off in the middle of a column."""
+    from test_host_scene import stitch_mips
+    sc = svo.scene
+    kw = dict(mip=0, palette=0, addx=0, addy=0, addz=0)
+    if case == "s1":
+        v = sc.generate(kind=1, depth=11, size=320, nblobs=3, seed=11)
+        path = str(tmp_path / "s1.rle4")
+        v.write_rle4(path, 320, 2048, 320)
+    elif case == "terrain_offsets_palette":
+        v = sc.generate(kind=2, depth=11, size=200, nblobs=0, seed=12)
+        path = str(tmp_path / "t.rle4")
+        v.write_rle4(path, 200, 1024, 200)
+        kw.update(palette=1, addx=100, addy=300, addz=777)
+    elif case == "mip1":
+        v0 = sc.generate(kind=2, depth=11, size=96, nblobs=0, seed=13)
+        v = sc.generate(kind=1, depth=10, size=160, nblobs=2, seed=14)
+        p0, p1, path = (str(tmp_path / n) for n in ("a.rle4", "b.rle4", "ab.rle4"))
+        v0.write_rle4(p0, 96, 2048, 96)
+        v.write_rle4(p1, 160, 1024, 160)
+        stitch_mips([p0, p1], path)
+        v0.free()
+        kw.update(mip=1)
+    else:
+        v = sc.generate(kind=1, depth=11, size=128, nblobs=1, seed=15)
+        full = str(tmp_path / "full.rle4")
+        v.write_rle4(full, 128, 2048, 128)
+        raw = open(full, "rb").read()
+        cut = (len(raw) - 20) * 3 // 5 // 2 * 2                       # keep the header's slab count: the stream simply ends early
+        path = str(tmp_path / "cut.rle4")
+        import struct
+        hdr = bytearray(raw[:20])
+        hdr[16:20] = struct.pack("<i", cut // 2)
+        open(path, "wb").write(bytes(hdr) + raw[20:20 + cut])
+    v.free()
+    host = sc.rle4_load(path, kw["palette"], kw["addx"], kw["addy"], kw["addz"], mip=kw["mip"])
+    exp, exp_root, st = sc.build_octree_voxels(host, depth=11)
+    nvox = len(host.arrays()[0])
+    host.free()
+    mem, root, dst = sc.octree_init_device(path, depth=11, **kw)
+    try:
+        assert dst["num_voxels"] == nvox and dst["num_unique"] == st["num_unique"]
+        assert root == exp_root and mem.size == exp.nbytes
+        assert np.array_equal(mem.to_numpy(), exp)
+    finally:
+        mem.free()
