@@ -110,6 +110,32 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa(index):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), so that the
+    page-locked frame buffers are allocated there and the per-frame read-back does not cross the socket interconnect.
+    Returns the CPU list used, or None (left alone) if anything about it cannot be determined."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                   # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return txt
+    except Exception:
+        return None
+
+
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this same
     command (profiles/ncu_traffic.json, written by tools/dram_summary.py); None if there is none."""
@@ -353,6 +379,7 @@ def main():
         print(json.dumps(line))
         return 0
 
+    host_cpus = pin_to_gpu_numa(local_rank)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -525,7 +552,7 @@ def main():
                            "hole_fraction_last_frame": hole_frac},
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
-                        "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum},
+                        "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus},
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

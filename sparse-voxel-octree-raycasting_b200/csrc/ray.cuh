@@ -137,7 +137,10 @@ __device__ __forceinline__ uint32_t colorize_word(uint32_t word)
 // CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
 // `stack` points at this thread's column of the shared [D+2][STRIDE] array (STRIDE = threads per CTA).
 // STRAIGHT selects the straight-line descent (see fetch_child): sparse, latency-bound launches.
-template <int D, int STRIDE = kRayBlock, bool STRAIGHT = false>
+#ifndef SVO_FULLSCREEN_STRAIGHT
+#define SVO_FULLSCREEN_STRAIGHT 0               // descent form of the full-screen launches (tools/variants.sh A/B)
+#endif
+template <int D, int STRIDE = kRayBlock, bool STRAIGHT = (SVO_FULLSCREEN_STRAIGHT != 0)>
 __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float *__restrict__ back,
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
                                             int idx, int idy, const RayCam &c, uint32_t *stack,

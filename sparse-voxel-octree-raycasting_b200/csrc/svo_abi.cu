@@ -474,7 +474,8 @@ static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes)
 {
     if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || getenv("SVO_NO_L2_PIN")) return;
     const size_t win = bytes < c->l2_window_max ? bytes : c->l2_window_max;
-    const size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
+    size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
+    if (getenv("SVO_L2_PIN_MB")) { const size_t cap = (size_t)atoi(getenv("SVO_L2_PIN_MB")) << 20; if (carve > cap) carve = cap; }
     CU_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
     cudaStreamAttrValue attr = {};
     attr.accessPolicyWindow.base_ptr = const_cast<void *>(oct);
@@ -545,7 +546,7 @@ static void do_fine_2(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t
                       int gx, int gy, int add_x, int add_y, const RayCam &cam)
 {
     if (gx <= 0 || gy <= 0) return;
-    dim3 grid((gx + 31) / 32, (gy + 7) / 8);
+    dim3 grid((gx + svo::kCtaW - 1) / svo::kCtaW, (gy + svo::kCtaH - 1) / svo::kCtaH);
     LAUNCH(c, "k_raycast_fine_2");
     if (c->depth == 11)
         k_raycast_fine_2<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
@@ -834,7 +835,12 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     float *back = (float *)backbuffer->dptr;
     uint32_t *idb = (uint32_t *)idbuffer->dptr;
     const uint32_t *oct = (const uint32_t *)octree->dptr;
-    pin_octree_in_l2(c, oct, octree->bytes);
+    // No persisting-L2 window for the octree here: the frame's own buffers (two 20 B/pixel frames, keys, image: ~100 MB at
+    // 1920x1024) want the whole 126 MB L2 -- with 31 MB set aside for the node pool the streaming passes write dirty lines
+    // back to DRAM that would otherwise have stayed put (6 475 -> 6 690 frames/s without the set-aside; the sparse rays
+    // lose 3 us).  SVO_FRAME_L2_PIN=1 restores it; the band kernels at 3840x2160 (buffers beyond any L2) keep it.
+    static const bool frame_pin = getenv("SVO_FRAME_L2_PIN") != nullptr;
+    if (frame_pin) pin_octree_in_l2(c, oct, octree->bytes);
 
     const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     ensure_key(c, n);
@@ -959,15 +965,17 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         }
         // :411-422 gap filter: reads the pre-filter frame (the destination slot: nothing writes it before the next frame's
         // resolve pass, which waits for this), writes the colorized image and the patch image
-        CU_CHECK(cudaStreamWaitEvent(c->stream3, c->ev_rays_done, 0));
+        static const bool fill_main = getenv("SVO_FILL_MAIN") != nullptr;
+        cudaStream_t sf = fill_main ? c->stream : c->stream3;
+        if (!fill_main) CU_CHECK(cudaStreamWaitEvent(sf, c->ev_rays_done, 0));
         {
-            LAUNCH_ON(c, "k_fill_list", c->stream3);
+            LAUNCH_ON(c, "k_fill_list", sf);
             const SnapView view = {dscreen, dscreen, (int)n};
-            k_fill_list<<<c->num_sms * 2, 256, 0, c->stream3>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
+            k_fill_list<<<c->num_sms * 2, 256, 0, sf>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
         }
-        CU_CHECK(cudaEventRecord(c->ev_fill_done, c->stream3));
+        CU_CHECK(cudaEventRecord(c->ev_fill_done, sf));
         c->fill_event_valid = true;
-        c->fill_outstanding = true;
+        c->fill_outstanding = !fill_main;
         c->patch_target = pingpong ? nullptr : dscreen;   // exact mode: buffer 0 still lacks the filtered words
         c->patch_count = fs.resid_count;
         c->patch_resid = fs.resid;

@@ -303,8 +303,16 @@ k_raycast_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const u
     }
 }
 
-// raycast_fine_2 (kernel/kernel.cl:846-942): the gx*gy rectangle at (add_x, add_y).  Each warp takes an
-// 8x4 pixel footprint; a CTA covers 32x8 pixels... (2x4 warps of 8x4... laid out 4 wide, 2 high).
+// raycast_fine_2 (kernel/kernel.cl:846-942): the gx*gy rectangle at (add_x, add_y).  Each warp takes a
+// kFootW x (32/kFootW) pixel footprint; the 8 warps of a CTA are laid out kCtaWarpsX wide.
+#ifndef SVO_FOOT_W
+#define SVO_FOOT_W 8
+#endif
+#ifndef SVO_CTA_WARPS_X
+#define SVO_CTA_WARPS_X 4
+#endif
+constexpr int kFootW = SVO_FOOT_W, kFootH = 32 / kFootW, kCtaWarpsX = SVO_CTA_WARPS_X, kCtaWarpsY = (kRayBlock / 32) / kCtaWarpsX;
+constexpr int kCtaW = kFootW * kCtaWarpsX, kCtaH = kFootH * kCtaWarpsY;      // pixels per CTA: 32 x 8
 template <int D>
 __global__ void __launch_bounds__(kRayBlock, SVO_RAY_MINBLOCKS)
 k_raycast_fine_2(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
@@ -312,8 +320,8 @@ k_raycast_fine_2(uint32_t *__restrict__ screen, float *__restrict__ back, const 
 {
     __shared__ uint32_t stack[(D + 2) * kRayBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
-    const int gx0 = blockIdx.x * 32 + lx, gy0 = blockIdx.y * 8 + ly;
+    const int lx = (warp % kCtaWarpsX) * kFootW + (lane % kFootW), ly = (warp / kCtaWarpsX) * kFootH + (lane / kFootW);
+    const int gx0 = blockIdx.x * kCtaW + lx, gy0 = blockIdx.y * kCtaH + ly;
     if (gx0 >= gx || gy0 >= gy) return;
     const int idx = gx0 + add_x, idy = gy0 + add_y;
     if (idx >= res_x || idy >= res_y) return;

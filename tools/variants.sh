@@ -8,6 +8,6 @@ mkdir -p build/variants
 while [ $# -ge 2 ]; do
   tag=$1; flags=$2; shift 2
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Xcompiler -fopenmp -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
-      -Xcompiler -fPIC,-O2 -Xptxas -v $flags -shared -o build/variants/libsvo_b200_$tag.so $PKG/csrc/svo_abi.cu $PKG/host/octree_builder.cpp $PKG/host/raycast_host.cpp $PKG/host/scene_io.cpp -Iinclude 2> build/variants/$tag.log
+      -Xcompiler -fPIC,-O2 -Xptxas -v $flags -shared -o build/variants/libsvo_b200_$tag.so $PKG/csrc/svo_abi.cu $PKG/csrc/svo_builder.cu $PKG/host/octree_builder.cpp $PKG/host/raycast_host.cpp $PKG/host/scene_io.cpp -Iinclude 2> build/variants/$tag.log
   grep -A1 "k_raycast_fine_2ILi11" build/variants/$tag.log | grep -o "Used [0-9]* registers" | head -1 | sed "s/^/$tag: /"
 done
