@@ -25,6 +25,10 @@ struct svo_ctx_s {
     // frame's reprojection pass; colorize + gap filter run on a third stream right after the rays
     cudaStream_t stream3 = nullptr;
     cudaEvent_t ev_scatter_done = nullptr, ev_rays_done = nullptr;
+    cudaStream_t stream4 = nullptr;         // split resolve: the gather pass runs here, beside the hole rays
+    cudaEvent_t ev_ids_done = nullptr, ev_gather_done = nullptr;
+    uint32_t *stage_s = nullptr; float *stage_b = nullptr;   // tile-ray staging (same pixel offsets as a frame; only the tile is touched)
+    size_t stage_pixels = 0;
     bool copy_pending = false;              // buffer 2 does not yet hold the last frame (materialize_copy)
     uint32_t *pend_src_s = nullptr, *pend_dst_s = nullptr;   // the pending copy: colour words ...
     float *pend_src_b = nullptr, *pend_dst_b = nullptr;      // ... and positions

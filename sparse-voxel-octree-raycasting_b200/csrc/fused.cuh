@@ -148,12 +148,22 @@ struct GatherArgs {
     Rect tile; int skip_tile; // tile rays run concurrently: leave colour / xyz of the tile rectangle to them
     ProjCam c;
     unsigned int *next_resid_count;
+    // != nullptr (split form): the tile rays have written their colour words / positions here (same pixel offsets) instead
+    // of into the destination, so that they can run before the destination is free; the gather pass moves them over
+    const uint32_t *stage_s; const float *stage_b;
 };
 
 // The destination was (logically) just cleared to holes, so a candidate is accepted iff its sz is below 0xffffff00
 // (kernel.cl:571 against an empty destination).
 __device__ __forceinline__ bool key_valid(unsigned long long k) { return k != kKeyEmpty && (uint32_t)(k >> 32) < 0xffffff00u; }
 
+// MODE 0: everything in one launch.  The split form takes the hole index list off the frame's critical path:
+// MODE 1 (ids): keys -> hole cells -> scan -> id buffer only (reads 8 B/pixel, writes the list), so the hole rays can start
+//               a dozen microseconds after the reprojection;
+// MODE 2 (gather): re-arm + depth-test resolve + gather + destination / image / gap-filter list, running BESIDE the hole
+//               rays on another stream.  It writes nothing into the 2x2 cells the rays fill (MODE 0 stores hole words there
+//               that the rays then overwrite), so the two never touch the same word; no tickets, no scan.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_resolve_gather(const GatherArgs a)
 {
@@ -167,12 +177,15 @@ k_resolve_gather(const GatherArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *__restrict__ dscreen = a.screen + a.dst0;
     float *__restrict__ dback = a.back + (size_t)a.dst0 * 4;
-    if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
-    __syncthreads();
-    const unsigned int ticket = ticket_s;
-    if (ticket == 0 && tid == 0) a.next_resid_count[0] = 0;   // re-arm the counter used two frames from now
+    if (MODE != 2) {
+        if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
+        __syncthreads();
+    }
+    const unsigned int ticket = MODE != 2 ? ticket_s : blockIdx.x;
+    if (MODE != 1 && ticket == 0 && tid == 0) a.next_resid_count[0] = 0;   // re-arm the counter used two frames from now
 
     if (ticket >= (unsigned)ncta) {
+        if (MODE == 1) return;                                   // (never launched: the id pass has no strip CTAs)
         // pixels outside the whole 16x16 blocks (right / bottom strips when the resolution is not a multiple of 16):
         // resolve only, they never enter the hole gather (kernel.cl:243-244)
         const int strip_cta = (int)ticket - ncta;
@@ -186,6 +199,12 @@ k_resolve_gather(const GatherArgs a)
             const unsigned long long k = a.key[p];
             if (k != kKeyEmpty) a.key[p] = kKeyEmpty;
             const bool v = key_valid(k), inr = a.skip_tile && in_rect(a.tile, x, y);
+            if (inr && a.stage_s) {                              // the tile ray's result, staged
+                const uint32_t w = a.stage_s[p];
+                dscreen[p] = w;
+                if (a.s.tex) a.s.tex[p] = colorize_word(w);
+                dback[p * 4] = a.stage_b[p * 4]; dback[p * 4 + 1] = a.stage_b[p * 4 + 1]; dback[p * 4 + 2] = a.stage_b[p * 4 + 2];
+            }
             if (v) {
                 const uint32_t srcofs = (uint32_t)k;
                 const uint32_t col = a.screen[srcofs];
@@ -245,9 +264,9 @@ k_resolve_gather(const GatherArgs a)
         }
         const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
         const unsigned long long tag = (unsigned long long)a.epoch << 34;
-        if (tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+        if (MODE != 2 && tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
 
-        if (active) {
+        if (MODE != 1 && active) {
             // all four gathers in flight before the first use
             uint32_t col[4]; float4 pc[4];
 #pragma unroll
@@ -258,6 +277,17 @@ k_resolve_gather(const GatherArgs a)
                     const uint32_t srcofs = (uint32_t)k[i];
                     col[i] = a.screen[srcofs];
                     pc[i] = *reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4);
+                }
+            }
+            const bool staged = a.stage_s != nullptr;
+            uint32_t scol[4] = {0, 0, 0, 0}; float4 spc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (staged && inr[i] && !(MODE == 2 && hole)) {
+                    const size_t q = pp[i >> 1] + (i & 1);
+                    scol[i] = a.stage_s[q];
+                    spc[i] = *reinterpret_cast<const float4 *>(a.stage_b + q * 4);      // w unused
                 }
             }
 #pragma unroll
@@ -278,20 +308,27 @@ k_resolve_gather(const GatherArgs a)
                         if (inr[i]) dback[(p + j) * 4 + 3] = phz;                 // the tile ray supplies colour and xyz, never w
                         else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
                     }
+                    if (staged && inr[i] && !(MODE == 2 && hole)) {               // ... from the staging buffers
+                        out[j] = scol[i];
+                        *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc[i].x, spc[i].y);
+                        dback[(p + j) * 4 + 2] = spc[i].z;
+                    }
                 }
-                if (even && !inr[2 * r] && !inr[2 * r + 1]) {
+                if (MODE == 2 && hole) continue;                              // the hole rays own this cell
+                const bool w0 = !inr[2 * r] || staged, w1 = !inr[2 * r + 1] || staged;
+                if (even && w0 && w1) {
                     *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
                     if (a.s.tex) *reinterpret_cast<uint2 *>(a.s.tex + p) = make_uint2(colorize_word(out[0]), colorize_word(out[1]));
                 } else {
-                    if (!inr[2 * r]) { dscreen[p] = out[0]; if (a.s.tex) a.s.tex[p] = colorize_word(out[0]); }
-                    if (!inr[2 * r + 1]) { dscreen[p + 1] = out[1]; if (a.s.tex) a.s.tex[p + 1] = colorize_word(out[1]); }
+                    if (w0) { dscreen[p] = out[0]; if (a.s.tex) a.s.tex[p] = colorize_word(out[0]); }
+                    if (w1) { dscreen[p + 1] = out[1]; if (a.s.tex) a.s.tex[p + 1] = colorize_word(out[1]); }
                 }
             }
         }
         // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
         // global atomic per CTA (a single counter hit by every pixel would serialise in L2)
         unsigned int rflags = 0;
-        if (active && !hole) {
+        if (MODE != 1 && active && !hole) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int px = x + (i & 1), py = y + (i >> 1);
@@ -302,9 +339,9 @@ k_resolve_gather(const GatherArgs a)
         unsigned int rofs = 0;
         if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
         __syncthreads();
-        if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
+        if (MODE != 1 && tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
         // decoupled look-back over the predecessors' aggregates (ticket order)
-        if (warp == 0) {
+        if (MODE != 2 && warp == 0) {
             uint32_t excl = 0;
             if (ticket > 0) {
                 int look = (int)ticket - 1;
@@ -335,8 +372,8 @@ k_resolve_gather(const GatherArgs a)
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
         }
-        const uint32_t cta_prefix = cta_prefix_s;
-        if (active) {
+        const uint32_t cta_prefix = MODE != 2 ? cta_prefix_s : 0u;
+        if (MODE != 2 && active) {
             const uint32_t ofs = cta_prefix + before_me;
             if ((warp & 1) == 0 && lane == 0) {
                 if (b > 0) a.idb[b] = my_block_cnt;                         // raycast_counthole :273 (word 0 becomes the total)
@@ -350,8 +387,9 @@ k_resolve_gather(const GatherArgs a)
                 o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
             }
         }
-        if (ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
+        if (MODE != 2 && ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
     }
+    if (MODE == 2) return;
     // the last CTA to finish re-arms the ticket counters for the next frame
     __syncthreads();
     if (tid == 0) {

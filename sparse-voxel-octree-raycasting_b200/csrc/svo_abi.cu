@@ -95,13 +95,17 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     c->num_sms = prop.multiProcessorCount;
     int prio_lo = 0, prio_hi = 0;
     CU_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, getenv("SVO_MAIN_HI") ? prio_hi : prio_lo));
+    // the main stream carries the frame's critical chain: its CTAs go first (SVO_MAIN_LO=1: below the side streams, -1.7 %)
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, getenv("SVO_MAIN_LO") ? prio_lo : prio_hi));
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_fill_done, cudaEventDisableTiming));
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, getenv("SVO_S3_LO") ? prio_lo : prio_hi));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_lo));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_ids_done, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_gather_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_scatter_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_rays_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
@@ -124,6 +128,11 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaStreamSynchronize(c->stream3);
     cudaStreamDestroy(c->stream3);
     cudaEventDestroy(c->ev_scatter_done); cudaEventDestroy(c->ev_rays_done);
+    cudaStreamSynchronize(c->stream4);
+    cudaStreamDestroy(c->stream4);
+    cudaEventDestroy(c->ev_ids_done); cudaEventDestroy(c->ev_gather_done);
+    if (c->stage_s) cudaFree(c->stage_s);
+    if (c->stage_b) cudaFree(c->stage_b);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
     cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_fill_done);
     if (c->patch.value) cudaFree(c->patch.value);
@@ -339,6 +348,7 @@ static void prof_flush(svo_ctx_t c)
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
     CU_CHECK(cudaStreamSynchronize(c->stream3));
+    CU_CHECK(cudaStreamSynchronize(c->stream4));
     c->timeline.clear();
     for (auto &r : c->prof_pending) {
         float ms = 0.f, t0 = 0.f;
@@ -809,6 +819,7 @@ extern "C" void svo_end_all_kernels(void)                             // src/ocl
     CU_CHECK(cudaStreamSynchronize(c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream2));
     CU_CHECK(cudaStreamSynchronize(c->stream3));
+    CU_CHECK(cudaStreamSynchronize(c->stream4));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -848,6 +859,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     if (c->patch_pixels < n) {
         if (c->patch.value) {
             CU_CHECK(cudaStreamSynchronize(c->stream)); CU_CHECK(cudaStreamSynchronize(c->stream2)); CU_CHECK(cudaStreamSynchronize(c->stream3));
+            CU_CHECK(cudaStreamSynchronize(c->stream4));
             CU_CHECK(cudaFree(c->patch.value));
         }
         CU_CHECK(cudaMalloc(&c->patch.value, (size_t)n * 4));
@@ -894,11 +906,33 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
         else do_memset(c, screen, n, kHole, n * 3);
     }
+    // Split resolve (default): the hole index list first (k_resolve_gather<1>, keys only), so the hole rays -- the longest
+    // link of the frame's critical chain -- start a dozen microseconds after the reprojection; the resolve/gather pass
+    // proper (<2>) runs beside them on the fourth stream and never writes the cells the rays fill.  The tile rays then
+    // write into staging buffers (they depend on nothing but the camera, so they start with the frame, beside the
+    // reprojection, instead of beside the hole rays) and the gather pass moves their pixels into the destination.
+    static const bool split_resolve = !getenv("SVO_NO_SPLIT_RESOLVE");
+    static const bool stage_tile = !getenv("SVO_NO_TILE_STAGING");
+    const bool split = split_resolve && overlap;
+    const bool staged = split && stage_tile;
+    if (staged && c->stage_pixels < n) {
+        if (c->stage_s) {
+            for (cudaStream_t st : {c->stream, c->stream2, c->stream3, c->stream4}) CU_CHECK(cudaStreamSynchronize(st));
+            CU_CHECK(cudaFree(c->stage_s)); CU_CHECK(cudaFree(c->stage_b));
+        }
+        CU_CHECK(cudaMalloc(&c->stage_s, (size_t)n * 4));
+        CU_CHECK(cudaMalloc(&c->stage_b, (size_t)n * 16));
+        c->stage_pixels = n;
+    }
     auto launch_tile = [&](cudaStream_t st) {                              // :361-387 tile refresh
         LAUNCH_ON(c, "k_rays_tile", st);
         const int grid = (((gx + 7) / 8) * ((gy + 3) / 4) * 32 + kRaysBlock - 1) / kRaysBlock;
-        if (c->depth == 11) k_rays_tile<11><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, fs);
-        else                k_rays_tile<14><<<grid, kRaysBlock, 0, st>>>(dscreen, dback, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, fs);
+        uint32_t *ts = staged ? c->stage_s : dscreen;
+        float *tb = staged ? c->stage_b : dback;
+        FusedScratch tfs = fs;
+        if (staged) tfs.tex = nullptr;                                     // the gather pass colorizes the staged words
+        if (c->depth == 11) k_rays_tile<11><<<grid, kRaysBlock, 0, st>>>(ts, tb, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, tfs);
+        else                k_rays_tile<14><<<grid, kRaysBlock, 0, st>>>(ts, tb, oct, octree_root, res_x, res_y, gx, gy, add_x, add_y, rc, tfs);
     };
     // A pending in-place gap-filter write of the previous frame is dead now: this frame rewrites all of buffer 0.
     c->patch_target = nullptr;
@@ -908,10 +942,10 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (c->fill_outstanding) { CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fill_done, 0)); c->fill_outstanding = false; }
     };
     bool tile_launched = false;
-    if (overlap && !from0) {
+    if (overlap && (!from0 || staged)) {
         // the tile rays depend on nothing of this frame: start them first (second stream, behind what the main stream has
         // done so far), concurrently with the reprojection
-        join_fill();
+        if (!staged) join_fill();                                          // (the filter reads the destination)
         CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
         launch_tile(c->stream2);
@@ -925,19 +959,36 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
                                                                   nsrc, from0 ? 2u * n : 0u, pc, from0 ? screen + 2 * (size_t)n : nullptr,
                                                                   from0 ? reinterpret_cast<float4 *>(back) + 2 * (size_t)n : nullptr);
     }
-    join_fill();
+    if (!split) join_fill();
     if (overlap && !tile_launched) {
         // the tile rays write buffer 0, which the pass above was still reading: they start beside the resolve pass
         CU_CHECK(cudaEventRecord(c->ev_scatter_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_scatter_done, 0));
+        if (c->fill_outstanding) CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fill_done, 0));   // (the filter reads buffer 0)
         launch_tile(c->stream2);
         CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
         tile_launched = true;
     }
-    {   // :157 clear + depth-test resolve + :272-315 hole gather, ids in the reference's order, idb[0] = idbuf_size
+    const GatherArgs ga = {screen, back, c->key, idb, fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc, next_resid_count,
+                           staged ? c->stage_s : nullptr, staged ? c->stage_b : nullptr};
+    if (split) {
+        {   // :272-315 hole gather from the keys alone, ids in the reference's order, idb[0] = idbuf_size
+            LAUNCH(c, "k_resolve_ids");
+            k_resolve_gather<1><<<(unsigned)ncta, 256, 0, c->stream>>>(ga);
+        }
+        CU_CHECK(cudaEventRecord(c->ev_ids_done, c->stream));
+        CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_ids_done, 0));                             // (re-arms the keys the id pass reads)
+        if (c->fill_outstanding) CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_fill_done, 0));   // (the filter reads buffer 0)
+        if (staged) CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_tile_done, 0));                // (moves the tile rays' pixels over)
+        {   // :157 clear + depth-test resolve + gather + image + gap-filter list
+            LAUNCH_ON(c, "k_resolve_gather", c->stream4);
+            k_resolve_gather<2><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream4>>>(ga);
+        }
+        CU_CHECK(cudaEventRecord(c->ev_gather_done, c->stream4));
+        join_fill();                                                                              // the hole rays write buffer 0 too
+    } else {   // :157 clear + depth-test resolve + :272-315 hole gather in one launch
         LAUNCH(c, "k_resolve_gather");
-        GatherArgs ga = {screen, back, c->key, idb, fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc, next_resid_count};
-        k_resolve_gather<<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
+        k_resolve_gather<0><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
     }
     {   // :332-359 hole rays, count on the device
         LAUNCH(c, "k_rays_holes");
@@ -948,6 +999,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     }
     if (tile_launched) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_tile_done, 0));
     else launch_tile(c->stream);
+    if (split) CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_gather_done, 0));
     if (!pingpong || tex) {
         // exact mode, lazy: the copy stays pending (see above).  The gap filter goes to the third stream, behind this
         // frame's rays; it reads the frame itself (buffer 0 == what buffer 2 will hold; the filter's in-place write is not
