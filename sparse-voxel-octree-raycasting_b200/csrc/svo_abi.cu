@@ -197,7 +197,13 @@ extern "C" svo_mem_t svo_malloc(size_t size, const void *host_ptr)
 extern "C" void svo_free(svo_mem_t m)
 {
     if (!m) return;
-    if (g_ctx) cudaStreamSynchronize(g_ctx->stream);
+    if (g_ctx) {
+        // nothing pending may outlive the buffer: the lazy cache copy / gap-filter write of the last fused frame are issued,
+        // then every stream of the context drains
+        flush_patches(g_ctx);
+        for (cudaStream_t st : {g_ctx->stream, g_ctx->stream2, g_ctx->stream3, g_ctx->stream4}) cudaStreamSynchronize(st);
+        if (g_ctx->copy_stream) cudaStreamSynchronize(g_ctx->copy_stream);
+    }
     cudaFree(m->dptr);
     delete m;
 }
@@ -252,7 +258,9 @@ extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, in
     if (!c) return;
     if (!src || size > src->bytes || slot < 0 || slot >= 4) { svo_fail(-108, "svo_present_async: bad arguments"); return; }
     if (!c->copy_stream) {
-        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        int plo = 0, phi = 0;                                          // the pack kernel is tiny and the read-back behind it is the
+        CU_CHECK(cudaDeviceGetStreamPriorityRange(&plo, &phi));        // longest transfer of the frame: never queue it behind a frame kernel
+        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, getenv("SVO_COPY_LO") ? plo : phi));
         for (int i = 0; i < 4; ++i) {
             CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
             CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
@@ -290,7 +298,9 @@ extern "C" void svo_present_rgb24_async(void *host_dst, svo_mem_t src, size_t np
     if (!c) return;
     if (!src || npixels * 4 > src->bytes || slot < 0 || slot >= 4) { svo_fail(-108, "svo_present_rgb24_async: bad arguments"); return; }
     if (!c->copy_stream) {
-        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        int plo = 0, phi = 0;                                          // the pack kernel is tiny and the read-back behind it is the
+        CU_CHECK(cudaDeviceGetStreamPriorityRange(&plo, &phi));        // longest transfer of the frame: never queue it behind a frame kernel
+        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, getenv("SVO_COPY_LO") ? plo : phi));
         for (int i = 0; i < 4; ++i) {
             CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
             CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
