@@ -244,9 +244,17 @@ def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, fr
             return float(t[0])
 
         if what == "raycast":
-            for p in P[:3]:
+            # SVO_FRAME_PINGPONG: consecutive full raycasts alternate between buffers 0 / 2 and between two streams, so one
+            # frame's tail (a few long rays) overlaps the next frame's bulk
+            R = []
+            for f in range(4 + frames):
+                rc.set_camera(*flythrough_pose(f))
+                q = rc.prepare_params(RX, RY, f)
+                q.flags |= ocl.FRAME_PINGPONG
+                R.append(q)
+            for p in R[:4]:
                 db.band.raycast(p)
-            ms = timed(db.band.raycast, P[4:4 + frames])
+            ms = timed(db.band.raycast, R[4:4 + frames])
         else:
             for p in P[:4]:                               # frames 0 and 1 are full raycasts through the hole path
                 db.band.frame(p)

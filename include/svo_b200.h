@@ -160,7 +160,9 @@ void svo_band_frame(svo_band_t band, const svo_frame_params *p);
 void svo_band_raycast(svo_band_t band, const svo_frame_params *p);
 void svo_band_sync(svo_band_t band);                       /* waits for this rank; reports a peer that never reached a barrier */
 /* svo_band_raycast leaves its end-of-frame barrier running beside the stream (consecutive full raycasts pipeline; the
- * writer keeps two frames, SVO_BAND_TEX reads the one completed last).  svo_band_join orders the stream behind it. */
+ * writer keeps two frames, SVO_BAND_TEX reads the one completed last).  svo_band_join orders the stream behind it.
+ * With SVO_FRAME_PINGPONG in p->flags consecutive raycasts also alternate between buffers 0 and 2 (svo_band_last_slot)
+ * and between two streams, so that one frame's tail overlaps the next frame's bulk; without it all land in buffer 0. */
 void svo_band_join(svo_band_t band);
 /* blocking access to this rank's buffers (SVO_BAND_*); id buffer layout: [0,Bl) counts ([0] = total), [Bl,2Bl) offsets, ids */
 int  svo_band_read(svo_band_t band, int which, void *dst, size_t bytes, size_t offset);

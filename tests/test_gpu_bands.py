@@ -112,6 +112,44 @@ def test_band_frames_pingpong(svo, orc, world, real, G, sr, res, nframes):
 
 
 @pytest.mark.parametrize("real", [False, True], ids=["virtual", "multi-gpu"])
+@pytest.mark.parametrize("G,sr", [(1, 0), (2, 16), (8, 16)])
+def test_band_full_raycast_pingpong(svo, orc, world, real, G, sr):
+    """SVO_FRAME_PINGPONG raycasts: consecutive frames alternate between buffers 0 and 2 (and between two streams, so that
+    they overlap) and between the writer's two frames.  Five frames are issued back to back; afterwards the last two
+    frames' hit words and positions sit in their slots and the image read back is the last frame's."""
+    octree, root = world
+    rx, ry = 320, 200
+    n = rx * ry
+    bs = svo.bands.LocalBandSet(devices_for(svo, G, real), octree, root, rx, ry, stripe_rows=sr)
+    try:
+        ref = []
+        for f in range(5):
+            cam = ofr.camera_args(*pose(f))
+            screen = np.full(4 * n, HOLE, dtype=np.uint32)
+            back = np.zeros(16 * n, dtype=np.float32)
+            orc.raycast_fine_2(screen, back, octree, root, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], gx=rx, gy=ry, threads=4)
+            ref.append((screen[:n].copy(), back[:4 * n].copy()))
+            svo.raycast.set_camera(*pose(f))
+            p = svo.raycast.prepare_params(rx, ry, 0)
+            p.flags |= svo.ocl.FRAME_PINGPONG
+            bs.raycast(p, sync=False)
+        bs.sync()
+        assert bs.bands[0].last_slot() == 0                      # frames 0, 2, 4 -> buffer 0; 1, 3 -> buffer 2
+        got_s, got_b = bs.assemble(slots=(0, 2))
+        for slot, f in ((0, 4), (2, 3)):
+            assert np.array_equal(got_s[slot * n:(slot + 1) * n], ref[f][0]), f"slot {slot}"
+            assert np.array_equal(got_b[slot * 4 * n:(slot + 1) * 4 * n].view(np.uint32).reshape(n, 4)[:, :3],
+                                  ref[f][1].view(np.uint32).reshape(n, 4)[:, :3]), f"slot {slot} xyz"
+        tex = np.zeros(n, dtype=np.uint32)
+        full = np.full(4 * n, HOLE, dtype=np.uint32)
+        full[:n] = ref[4][0]
+        orc.raycast_colorize(full, tex, rx, ry)
+        assert np.array_equal(bs.frame_image(), tex)
+    finally:
+        bs.close()
+
+
+@pytest.mark.parametrize("real", [False, True], ids=["virtual", "multi-gpu"])
 @pytest.mark.parametrize("G,sr", [(1, 0), (2, 0), (4, 16), (8, 16)])
 def test_band_full_raycast(svo, orc, world, real, G, sr):
     """Banded full raycast (BASELINE.json config 3): hit words, positions and the colorized frame of a full-screen
