@@ -358,6 +358,8 @@ def main():
     ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
     ap.add_argument("--ray-stripe-rows", type=int, default=16, help="stripe height of the banded full raycast at 3840x2160")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (bands at 3840x2160, 64-camera batch, depth-14 terrain)")
+    ap.add_argument("--distinct-paths", action="store_true",
+                    help="view-parallel ranks render different camera paths (default: every rank renders the config-2 flythrough, so the work per GPU is fixed as N grows)")
     ap.add_argument("--bands-only", action="store_true", help="only the 3840x2160 screen-band measurements (development aid)")
     ap.add_argument("--mode", default="fused", choices=["fused", "pingpong"],
                     help="fused: every buffer as the reference leaves it (cache copy kept); pingpong: SVO_FRAME_PINGPONG, no cache copy")
@@ -413,7 +415,7 @@ def main():
     n = RES_X * RES_Y
 
     def params(f):
-        rc.set_camera(*flythrough_pose(f, cam_id=rank))
+        rc.set_camera(*flythrough_pose(f, cam_id=rank if args.distinct_paths else 0))
         return rc.prepare_params(RES_X, RES_Y, f)
 
     total = args.warmup + args.steps
@@ -480,11 +482,28 @@ def main():
     sampler.stop_flag = True
     sampler.join()
     checksum = int(np.frombuffer(host_frame, dtype=np.uint8, count=n * 3).sum(dtype=np.uint64))
+    # the box's plain device -> pinned-host copy rate, to read the e2e figure against (it moves n*3 bytes per frame over this link;
+    # measured: 35-50 GB/s on most boxes of the pool, ~12 GB/s on some, where e2e then sits at ~2 000 frames/s whatever the GPU does)
+    try:
+        dsrc = torch.empty(64 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        hdst = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+        hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            hdst.copy_(dsrc, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        d2h_gbs = 4 * (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del dsrc, hdst
+    except Exception:
+        d2h_gbs = None
 
     # ---- full-screen primary rays (BASELINE.json config 1): raycast_fine_2 over the whole screen ----
     ray_ms = []
     for f in (0, 40, 80, 120, 160, 200):
-        rc.set_camera(*flythrough_pose(f, cam_id=rank))
+        rc.set_camera(*flythrough_pose(f, cam_id=rank if args.distinct_paths else 0))
         ray_ms.append(rc.full_raycast_ms(RES_X, RES_Y))
     mrays = n / (np.median(ray_ms) * 1e-3) / 1e6
 
@@ -555,13 +574,14 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
                 "config": {"workload": workload_name(scene_name),
                            "octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
-                           "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} (one camera path per GPU, no communication)",
+                           "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} ({'a different camera path' if args.distinct_paths else 'the config-2 flythrough'} on every GPU, octree replicated, no communication)",
                            "l2_note": "working set per frame (2 x 20 B/pixel x 1.97 Mpixel + octree) exceeds nothing by construction: inputs change every frame; "
                                       "no L2 flush between frames (a frame reads what the previous frame wrote, as in the real pipeline)",
                            "hole_fraction_last_frame": hole_frac},
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
-                        "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus},
+                        "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus,
+                        "d2h_link_gbs": d2h_gbs, "d2h_used_gbs": e2e_fps / world * n * 3 / 1e9},
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -13,3 +13,14 @@ print("n=$N fps", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "mra
       "| bands mrays", round(b.get("full_raycast_mrays_per_s", 0), 1), "ms", round(b.get("full_raycast_ms", 0), 4), "warped fps", round(b.get("warped_fps", 0), 1),
       "| 64cam Grays/s", round(d.get("view_parallel_64_cameras", {}).get("grays_per_s", 0), 2))
 PY
+if [ -n "$WITH_N1" ]; then
+  timeout 600 python bench.py --gpus 1 --no-cpu-baseline > gpurun_out/scale_n1_on$N.json 2> gpurun_out/scale_n1_on$N.err
+  python - <<PY
+import json
+d = json.loads(open("gpurun_out/scale_n1_on$N.json").read().strip().splitlines()[-1])
+b = d.get("bands_3840x2160", {})
+print("n=1 (same box) fps", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "mrays", round(d["full_raycast_mrays_per_s"], 1),
+      "| bands mrays", round(b.get("full_raycast_mrays_per_s", 0), 1), "ms", round(b.get("full_raycast_ms", 0), 4), "warped fps", round(b.get("warped_fps", 0), 1),
+      "| 64cam Grays/s", round(d.get("view_parallel_64_cameras", {}).get("grays_per_s", 0), 2))
+PY
+fi
