@@ -30,6 +30,9 @@ void svo_raycast_set_camera(const float pos[3], const float rot[3]);
 void svo_raycast_draw(int res_x, int res_y, int sync);
 int  svo_raycast_frame(void);                      /* frame counter of the last draw (first frame = 0) */
 void svo_raycast_reset(void);                      /* frame counter back to -1 (next draw is frame 0: full raycast) */
+/* SVO_MODE_REFERENCE only: copy target ((frame>>4)%2)+1, the variant the reference keeps in a comment at src/raycast.h:395,
+ * instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames.  0 = ok. */
+int  svo_raycast_set_cache_rotation(int on);
 int  svo_raycast_idbuf_size(void);                 /* hole-ray count of the last frame (:298) */
 /* the camera block the last draw used: v0[4], rows[3][4], cols[3][4] (28 floats) -- for parity harnesses */
 void svo_raycast_last_camera(float out28[28]);

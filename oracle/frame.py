@@ -63,7 +63,10 @@ def camera_args(pos, rot, depth=11):
 class OracleFrame:
     """State of the reference's frame loop (4 colour + 4 coordinate buffers, id buffer, frame counter)."""
 
-    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11):
+    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11, cache_rotation=False):
+        """cache_rotation: the copy target the reference has in a comment, `((frame>>4)%2)+1` (src/raycast.h:395), instead of
+        the hard-wired 2 -- the variant that makes the triple buffer real."""
+        self.cache_rotation = cache_rotation
         self.o, self.octree, self.root = orc, octree, root
         self.res_x, self.res_y, self.threads, self.depth = res_x, res_y, threads, depth
         n = res_x * res_y
@@ -108,9 +111,10 @@ class OracleFrame:
                          v0, *cam["cols"], threads=t)
         if stop_after == "rays":
             return cam
-        o.memcpy(self.screen, 2 * n, self.screen, 0, n)                 # :394-405, target = 2
+        target = ((frame >> 4) % 2) + 1 if self.cache_rotation else 2   # :395
+        o.memcpy(self.screen, target * n, self.screen, 0, n)            # :394-405
         back_u = self.back.view(np.uint32)
-        o.memcpy(back_u, 2 * n * 4, back_u, 0, n * 4)
+        o.memcpy(back_u, target * n * 4, back_u, 0, n * 4)
         if stop_after == "copy":
             return cam
         o.raycast_fillhole2(self.screen, rx, ry, frame)                 # :411-422

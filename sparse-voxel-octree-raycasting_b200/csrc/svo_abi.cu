@@ -102,7 +102,7 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_fill_done, cudaEventDisableTiming));
-    CU_CHECK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, getenv("SVO_S3_LO") ? prio_lo : prio_hi));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_lo));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_ids_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_gather_done, cudaEventDisableTiming));
@@ -260,7 +260,7 @@ extern "C" void svo_present_async(void *host_dst, svo_mem_t src, size_t size, in
     if (!c->copy_stream) {
         int plo = 0, phi = 0;                                          // the pack kernel is tiny and the read-back behind it is the
         CU_CHECK(cudaDeviceGetStreamPriorityRange(&plo, &phi));        // longest transfer of the frame: never queue it behind a frame kernel
-        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, getenv("SVO_COPY_LO") ? plo : phi));
+        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, phi));
         for (int i = 0; i < 4; ++i) {
             CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
             CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
@@ -300,7 +300,7 @@ extern "C" void svo_present_rgb24_async(void *host_dst, svo_mem_t src, size_t np
     if (!c->copy_stream) {
         int plo = 0, phi = 0;                                          // the pack kernel is tiny and the read-back behind it is the
         CU_CHECK(cudaDeviceGetStreamPriorityRange(&plo, &phi));        // longest transfer of the frame: never queue it behind a frame kernel
-        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, getenv("SVO_COPY_LO") ? plo : phi));
+        CU_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, phi));
         for (int i = 0; i < 4; ++i) {
             CU_CHECK(cudaEventCreateWithFlags(&c->present_ready[i], cudaEventDisableTiming));
             CU_CHECK(cudaEventCreateWithFlags(&c->present_done[i], cudaEventDisableTiming));
@@ -494,8 +494,7 @@ static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes)
 {
     if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || getenv("SVO_NO_L2_PIN")) return;
     const size_t win = bytes < c->l2_window_max ? bytes : c->l2_window_max;
-    size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
-    if (getenv("SVO_L2_PIN_MB")) { const size_t cap = (size_t)atoi(getenv("SVO_L2_PIN_MB")) << 20; if (carve > cap) carve = cap; }
+    const size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
     CU_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
     cudaStreamAttrValue attr = {};
     attr.accessPolicyWindow.base_ptr = const_cast<void *>(oct);
@@ -1027,9 +1026,8 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         }
         // :411-422 gap filter: reads the pre-filter frame (the destination slot: nothing writes it before the next frame's
         // resolve pass, which waits for this), writes the colorized image and the patch image
-        static const bool fill_main = getenv("SVO_FILL_MAIN") != nullptr;
-        cudaStream_t sf = fill_main ? c->stream : c->stream3;
-        if (!fill_main) CU_CHECK(cudaStreamWaitEvent(sf, c->ev_rays_done, 0));
+        cudaStream_t sf = c->stream3;
+        CU_CHECK(cudaStreamWaitEvent(sf, c->ev_rays_done, 0));
         {
             LAUNCH_ON(c, "k_fill_list", sf);
             const SnapView view = {dscreen, dscreen, (int)n};
@@ -1037,7 +1035,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         }
         CU_CHECK(cudaEventRecord(c->ev_fill_done, sf));
         c->fill_event_valid = true;
-        c->fill_outstanding = !fill_main;
+        c->fill_outstanding = true;
         c->patch_target = pingpong ? nullptr : dscreen;   // exact mode: buffer 0 still lacks the filtered words
         c->patch_count = fs.resid_count;
         c->patch_resid = fs.resid;

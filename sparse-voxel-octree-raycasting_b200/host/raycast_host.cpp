@@ -23,6 +23,7 @@ struct State {
     uint32_t octree_root_normal = 0;
     int octree_depth = 11;
     int frame = -1;                                 // static int frame=-1  :104
+    bool cache_rotation = false;                    // copy target ((frame>>4)%2)+1 instead of 2 (:395), reference mode only
     float pos[3] = {1.f, 50.f, 1.f};                // static vec3f pos(1,50,1)  :113
     float rot[3] = {0.0001f, 0.f, 0.f};             // vec3f rot(0.0001,0,0)     :114
     int idbuf_size = 0;
@@ -98,6 +99,12 @@ extern "C" void svo_raycast_set_camera(const float pos[3], const float rot[3])
 
 extern "C" int svo_raycast_frame(void) { return S.frame; }
 extern "C" void svo_raycast_reset(void) { S.frame = -1; }
+extern "C" int svo_raycast_set_cache_rotation(int on)
+{
+    if (on && S.mode != SVO_MODE_REFERENCE) return -1;      // the fused frame implements the shipped copy target (2)
+    S.cache_rotation = on != 0;
+    return 0;
+}
 extern "C" int svo_raycast_idbuf_size(void) { return S.mode == SVO_MODE_REFERENCE ? S.idbuf_size : svo_frame_idbuf_size(); }
 extern "C" void svo_raycast_last_camera(float out28[28]) { memcpy(out28, S.cam, sizeof S.cam); }
 
@@ -177,7 +184,7 @@ extern "C" void svo_raycast_draw(int res_x, int res_y, int sync)
         svo_param(4, &fovx); svo_param(4, &fovy);
         svo_end();
     }
-    const int target = 2;                                                        // :395
+    const int target = S.cache_rotation ? ((frame >> 4) % 2) + 1 : 2;            // :395
     svo_memcpy(S.mem_screenbuffer, (uint32_t)size_col * target, S.mem_screenbuffer, 0, (uint32_t)size_col);   // :396-399
     svo_memcpy(S.mem_backbuffer, (uint32_t)size_xyz * target, S.mem_backbuffer, 0, (uint32_t)size_xyz);       // :401-404
     svo_begin(&S.k_fillhole2, res_x, res_y, 16, 16);                             // :414-421

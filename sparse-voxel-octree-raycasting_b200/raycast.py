@@ -67,8 +67,13 @@ def wrap_pos(pos, depth=None):
     return (p / f32(16.0)).astype(np.float32)
 
 
-def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth=11, device=0, mode="fused"):
-    """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree)."""
+def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth=11, device=0, mode="fused", cache_rotation=False):
+    """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree).
+    cache_rotation (launch-by-launch "reference" mode only): copy target `((frame>>4)%2)+1`, the variant the reference keeps
+    in a comment at src/raycast.h:395, instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames."""
+    if cache_rotation and mode != "reference":
+        raise ValueError("cache_rotation needs mode='reference' (the fused frame implements the shipped copy target, 2)")
+    S.cache_rotation = bool(cache_rotation)
     global WINDOW_WIDTH_MAX, WINDOW_HEIGHT_MAX, OCTREE_DEPTH
     if max_w:
         WINDOW_WIDTH_MAX = max_w
@@ -201,7 +206,7 @@ def raycast_draw(res_x, res_y):
         ocl.ocl_param(a)
     ocl.ocl_param(fl(fovx)); ocl.ocl_param(fl(fovy))
     ocl.ocl_end()
-    target = 2                                                                     # :395
+    target = ((frame >> 4) % 2) + 1 if getattr(S, "cache_rotation", False) else 2  # :395
     ocl.ocl_memcpy(S.mem_screenbuffer, size_col * target, S.mem_screenbuffer, 0, size_col)   # :396-399
     ocl.ocl_memcpy(S.mem_backbuffer, size_xyz * target, S.mem_backbuffer, 0, size_xyz)       # :401-404
     ocl.ocl_begin(_kernel("raycast_fillhole2"), res_x, res_y, 16, 16)              # :414-421

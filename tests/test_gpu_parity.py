@@ -346,6 +346,65 @@ def test_present_rgb24(svo, orc, world, res):
         svo.ocl_init(0)
 
 
+@pytest.mark.parametrize("mode", ["fused", "pingpong"])
+def test_schedule_switches(svo, mode):
+    """The A/B switches of the fused frame's schedule only move work between streams and launches:
+    every combination must leave bit-identical buffers, ids and images.  The default schedule is the one the other tests
+    pin against the oracle; here each switch runs the same 12 back-to-back frames in a process of its own (the switches are
+    read once per process) and its digest is compared with the default's."""
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_schedule_worker.py")
+
+    def run(extra):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("SVO_")}
+        env.update(extra)
+        out = subprocess.run([sys.executable, worker, mode, "320", "192", "12"], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][-1].split()
+        return line[1], int(line[2])
+
+    ref, deferred = run({})
+    assert deferred == (10 if mode == "fused" else 0)          # frames 2..11 carried the previous frame's cache copy
+    for extra in ({"SVO_NO_SPLIT_RESOLVE": "1"}, {"SVO_NO_TILE_STAGING": "1"}, {"SVO_NO_LAZY_COPY": "1"}, {"SVO_NO_OVERLAP": "1"},
+                  {"SVO_NO_LAZY_COPY": "1", "SVO_NO_SPLIT_RESOLVE": "1"}, {"SVO_FRAME_L2_PIN": "1"}, {"SVO_MAIN_LO": "1"},
+                  {"SVO_HOLES_SMAX": "1"}):
+        got, _ = run(extra)
+        assert got == ref, f"{extra} changes the result"
+
+
+def test_cache_rotation_reference_mode(svo, orc, world):
+    """The copy target the reference keeps in a comment (`((frame>>4)%2)+1`, src/raycast.h:395): cache
+    buffers 1 and 2 alternate every 16 frames, so both reprojection launches see real frames and depth ties between them
+    occur (buffer 1 wins: the earlier launch).  Launch-by-launch mode against the oracle, 40 frames, every buffer."""
+    octree, root = world
+    rx, ry = 320, 192
+    n = rx * ry
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4, cache_rotation=True)
+    rc = svo.raycast
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="reference", cache_rotation=True)
+    try:
+        for f in range(40):
+            pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
+            O.draw(pos, rot)
+            rc.set_camera(pos, rot)
+            rc.raycast_draw(rx, ry)
+            screen, back, idb = rc.read_buffers(rx, ry)
+            assert rc.idbuf_size() == O.idbuf_size, f"frame {f}"
+            assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"frame {f} ids"
+            assert np.array_equal(screen, O.screen[:4 * n]), f"frame {f} colour"
+            assert np.array_equal(back.view(np.uint32), O.back[:16 * n].view(np.uint32)), f"frame {f} xyz"
+            assert np.array_equal(rc.read_frame(rx, ry).ravel(), O.tex), f"frame {f} tex"
+        assert np.any(O.screen[n:2 * n] != HOLE) and np.any(O.screen[2 * n:3 * n] != HOLE)      # both caches are live
+        with pytest.raises(ValueError):
+            rc.raycast_exit()
+            rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused", cache_rotation=True)
+    finally:
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
 def test_golden_frames(svo):
     """The CUDA path against the committed vectors produced by the reference's own source (tests/golden)."""
     from golden.make_golden import golden_pose, NFRAMES

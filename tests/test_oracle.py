@@ -81,6 +81,23 @@ def test_frame_sequence_matches_reference(orc, ref, pose):
         assert np.array_equal(A.tex, B.tex)
 
 
+def test_frame_sequence_cache_rotation_matches_reference(orc, ref):
+    """Copy target ((frame>>4)%2)+1 (the commented variant at src/raycast.h:395): over 36 frames both cache buffers hold real
+    frames and both reprojection launches contribute; the C restatement follows the reference source executed by the shim."""
+    octree, root = ref.build_octree(*scenes.small_world())
+    rx, ry = 96, 64
+    A = fr.OracleFrame(ref, octree, root, rx, ry, threads=4, cache_rotation=True)
+    B = fr.OracleFrame(orc, octree, root, rx, ry, threads=4, cache_rotation=True)
+    for f in range(36):
+        p, r = (10 + 0.3 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.012 * f, 0.0)
+        A.draw(p, r); B.draw(p, r)
+        assert np.array_equal(A.screen, B.screen), f"frame {f}"
+        assert np.array_equal(A.back.view(np.uint32), B.back.view(np.uint32)), f"frame {f}"
+        assert np.array_equal(A.tex, B.tex), f"frame {f}"
+    n = rx * ry
+    assert np.any(A.screen[n:2 * n] != 0xFFFFFF00) and np.any(A.screen[2 * n:3 * n] != 0xFFFFFF00)
+
+
 def test_fillhole2_snapshot_random_images(orc, ref):
     rng = np.random.RandomState(5)
     rx, ry = 80, 48
