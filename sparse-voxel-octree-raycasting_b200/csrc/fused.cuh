@@ -1,20 +1,22 @@
-// fused.cuh -- the B200-native frame: the reference's 13-launch frame (src/raycast.h:147-438) as 6 launches on two
-// streams with no host round trip.
+// fused.cuh -- the B200-native frame: the reference's 13-launch frame (src/raycast.h:147-438) as three launches on the
+// critical stream plus three on side streams, with no host round trip (schedule: DESIGN.md section 4a, svo_frame_fused).
 //
-//   k_proj_scatter2   both reprojection launches (:177-198) -> 64-bit atomicMin keys (depth | source offset)
-//   k_resolve_gather  clear (:157) + depth-test resolve + raycast_counthole / sumids / writeids (:272-315) in one pass
-//                     over the keys: one thread per 2x2 cell, warp ballots per 16x16 block, decoupled look-back scan
-//                     across CTAs in ticket order (= block order, so the id order is the reference's); also lists the
-//                     hole pixels no ray will fill (input of the gap filter)
-//   k_rays_tile       raycast_fine_2 tile refresh (:361-387); independent of the reprojection, so it runs on a second
-//                     stream concurrently with the two kernels above
-//   k_rays_holes      raycast_holes (:332-359); idbuf_size is read on the device
-//   k_copy_colorize   cache copy (:394-405) + raycast_colorize (:429-437), pure streaming
-//   k_fill_list       raycast_fillhole2 (:411-422), snapshot semantics, on the listed hole pixels only: reads the cache copy
-//                     just made, writes the filtered word to the colorized image and keeps it; second stream, off the
-//                     critical path of the next frame
-//   k_apply_patches   the filter's in-place write into buffer 0, issued only when the host can observe buffer 0 before
-//                     the next frame rewrites it (sync, read-back, launch-API use)
+//   k_proj_scatter2      both reprojection launches (:177-198) -> 64-bit atomicMin keys (depth | source offset); in steady
+//                        state it also carries the PREVIOUS frame's cache copy (:394-405): the frame is read once
+//   k_resolve_gather<1>  raycast_counthole / sumids / writeids (:272-315) from the keys alone: one thread per 2x2 cell, warp
+//                        ballots per 16x16 block, decoupled look-back scan across CTAs in ticket order (= block order, so
+//                        the id order is the reference's)
+//   k_rays_holes         raycast_holes (:332-359); idbuf_size is read on the device
+//   k_resolve_gather<2>  clear (:157) + depth-test resolve + gather + destination + raycast_colorize (:429-437) of what it
+//                        writes + the tile rays' staged pixels + the list of hole pixels no ray will fill; fourth stream,
+//                        beside the hole rays (<0> = <1> and <2> in one launch)
+//   k_rays_tile          raycast_fine_2 tile refresh (:361-387); depends on nothing but the camera: second stream, into
+//                        staging buffers, from the start of the frame
+//   k_fill_list          raycast_fillhole2 (:411-422), snapshot semantics, on the listed hole pixels only: reads the finished
+//                        frame, writes the filtered word to the colorized image and the patch image; third stream, beside
+//                        the next frame's reprojection
+//   k_copy_colorize      the plain cache copy, k_apply_patches the filter's in-place write into buffer 0: issued only when
+//                        the host can observe the buffers before the next frame rewrites them (sync, read-back, launch API)
 //
 // Buffer roles are parameters (slot = buffer index in the reference's 4-buffer arrays):
 //   exact mode      sources = slots 1 and 2, destination = slot 0, copy target = slot 2: every buffer ends the frame
