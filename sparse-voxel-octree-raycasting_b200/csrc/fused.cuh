@@ -116,28 +116,39 @@ __device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, i
 // follows with nothing having observed the buffers in between, this kernel reads the previous frame out of buffer 0
 // ONCE (20 B/pixel), stores it into buffer 2 and projects it in the same pass.  `key_bias` (2N) makes the keys name the
 // pixels of buffer 2, which is where the resolve pass gathers from -- same words, same keys as copy-then-project.
+#ifndef SVO_SCATTER_PIX
+#define SVO_SCATTER_PIX 1            // source pixels per thread (loads of all of them in flight before the first use)
+#endif
+constexpr int kScatterPix = SVO_SCATTER_PIX;
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
                 int res_x, int res_y, unsigned int src0, unsigned int nsrc, unsigned int key_bias, ProjCam c,
                 uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b)
 {
-    const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nsrc) return;
-    const uint32_t srcofs = q + src0;
-    const uint32_t word = __ldg(screen + srcofs);
-    float4 pc;
-    if (copy_s) {                                        // the copy takes every pixel, holes and their stale positions included
-        pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
-        copy_s[q] = word;
-        copy_b[q] = pc;
-        if (word == kHole) return;
-    } else {
-        if (word == kHole) return;
-        pc = __ldg(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t word[kScatterPix]; float4 pc[kScatterPix]; bool live[kScatterPix];
+#pragma unroll
+    for (int i = 0; i < kScatterPix; ++i) {
+        const unsigned int q = q0 + i * stride;
+        live[i] = q < nsrc;
+        word[i] = kHole; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[i]) {
+            word[i] = __ldg(screen + q + src0);
+            // the copy takes every pixel, holes and their stale positions included; the projection alone skips the holes
+            if (copy_s || word[i] != kHole) pc[i] = __ldg(reinterpret_cast<const float4 *>(back + (size_t)(q + src0) * 4));
+        }
     }
-    int sx, sy; float phz;
-    if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) return;
-    atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (srcofs + key_bias));
+#pragma unroll
+    for (int i = 0; i < kScatterPix; ++i) {
+        const unsigned int q = q0 + i * stride;
+        if (!live[i]) continue;
+        if (copy_s) { copy_s[q] = word[i]; copy_b[q] = pc[i]; }
+        if (word[i] == kHole) continue;
+        int sx, sy; float phz;
+        if (!proj_point_fast(c, pc[i].x, pc[i].y, pc[i].z, res_x, res_y, sx, sy, phz)) continue;
+        atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (q + src0 + key_bias));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -964,7 +964,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = from0 ? n : (unsigned int)src_count * n;
-        k_proj_scatter2<<<(nsrc + 255) / 256, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
+        k_proj_scatter2<<<(nsrc + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
                                                                   nsrc, from0 ? 2u * n : 0u, pc, from0 ? screen + 2 * (size_t)n : nullptr,
                                                                   from0 ? reinterpret_cast<float4 *>(back) + 2 * (size_t)n : nullptr);
     }
