@@ -29,6 +29,21 @@
 
 namespace svo {
 
+// Loads of the streaming passes that run beside a ray kernel (reprojection beside the tile rays, gather beside the hole rays):
+// every word is used once, so they go through L2 only (.cg) and leave L1 to the rays' node fetches.
+#ifndef SVO_STREAM_LDCG
+#define SVO_STREAM_LDCG 1
+#endif
+template <class T>
+__device__ __forceinline__ T ld_stream(const T *p)
+{
+#if SVO_STREAM_LDCG
+    return __ldcg(p);
+#else
+    return __ldg(p);
+#endif
+}
+
 struct FusedScratch {
     unsigned long long *scan_state;   // per CTA ticket: epoch<<34 | flag<<32 | value
     unsigned int *counters;           // [0] ticket, [1] done, [4..7] residual-hole counts (rotating over 4 frames)
@@ -134,9 +149,9 @@ k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ b
         live[i] = q < nsrc;
         word[i] = kHole; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live[i]) {
-            word[i] = __ldg(screen + q + src0);
+            word[i] = ld_stream(screen + q + src0);
             // the copy takes every pixel, holes and their stale positions included; the projection alone skips the holes
-            if (copy_s || word[i] != kHole) pc[i] = __ldg(reinterpret_cast<const float4 *>(back + (size_t)(q + src0) * 4));
+            if (copy_s || word[i] != kHole) pc[i] = ld_stream(reinterpret_cast<const float4 *>(back + (size_t)(q + src0) * 4));
         }
     }
 #pragma unroll
@@ -254,9 +269,9 @@ k_resolve_gather(const GatherArgs a)
                 const size_t p = (size_t)(y + r) * res_x + x;
                 pp[r] = p;
                 if (even) {
-                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(a.key + p);
+                    const ulonglong2 kk = ld_stream(reinterpret_cast<const ulonglong2 *>(a.key + p));
                     k[2 * r] = kk.x; k[2 * r + 1] = kk.y;
-                } else { k[2 * r] = a.key[p]; k[2 * r + 1] = a.key[p + 1]; }
+                } else { k[2 * r] = ld_stream(a.key + p); k[2 * r + 1] = ld_stream(a.key + p + 1); }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) valid[i] = key_valid(k[i]);
@@ -288,8 +303,8 @@ k_resolve_gather(const GatherArgs a)
                 col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid[i]) {
                     const uint32_t srcofs = (uint32_t)k[i];
-                    col[i] = a.screen[srcofs];
-                    pc[i] = *reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4);
+                    col[i] = ld_stream(a.screen + srcofs);
+                    pc[i] = ld_stream(reinterpret_cast<const float4 *>(a.back + (size_t)srcofs * 4));
                 }
             }
             const bool staged = a.stage_s != nullptr;
@@ -299,8 +314,8 @@ k_resolve_gather(const GatherArgs a)
                 spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (staged && inr[i] && !(MODE == 2 && hole)) {
                     const size_t q = pp[i >> 1] + (i & 1);
-                    scol[i] = a.stage_s[q];
-                    spc[i] = *reinterpret_cast<const float4 *>(a.stage_b + q * 4);      // w unused
+                    scol[i] = ld_stream(a.stage_s + q);
+                    spc[i] = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + q * 4));      // w unused
                 }
             }
 #pragma unroll
