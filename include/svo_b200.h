@@ -119,6 +119,11 @@ enum { SVO_FRAME_PINGPONG = 1 };
  * After it returns every buffer holds what the reference sequence would have left there. */
 void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t idbuffer, svo_mem_t octree,
                      uint32_t octree_root, svo_mem_t screenbuffer_tex, const svo_frame_params *p);
+/* A batch of full-screen raycasts of one scene (raycast_fine_2 with add = 0 and global = res_x x res_y, kernel.cl:846-942):
+ * camera i goes into buffer 0 (i even) or buffer 2 (i odd) of the 4-buffer arrays, on two alternating streams, so that
+ * consecutive cameras overlap.  Only v0, cols, fovx, fovy of each entry are used.  Asynchronous. */
+void svo_raycast_batch(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t octree, uint32_t octree_root,
+                       int res_x, int res_y, int ncams, const svo_frame_params *cams);
 /* idbuf_size of the last fused frame (the value the reference reads back at src/raycast.h:298); blocking */
 int  svo_frame_idbuf_size(void);
 /* buffer index (0 or 2) the last fused frame was rendered into; always 0 without SVO_FRAME_PINGPONG */

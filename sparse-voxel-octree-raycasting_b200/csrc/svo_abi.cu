@@ -562,15 +562,16 @@ static void do_holes(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t 
 }
 
 static void do_fine_2(svo_ctx_t c, uint32_t *screen, float *back, const uint32_t *oct, uint32_t root, int res_x, int res_y,
-                      int gx, int gy, int add_x, int add_y, const RayCam &cam)
+                      int gx, int gy, int add_x, int add_y, const RayCam &cam, cudaStream_t st = nullptr)
 {
     if (gx <= 0 || gy <= 0) return;
+    if (!st) st = c->stream;
     dim3 grid((gx + svo::kCtaW - 1) / svo::kCtaW, (gy + svo::kCtaH - 1) / svo::kCtaH);
-    LAUNCH(c, "k_raycast_fine_2");
+    LAUNCH_ON(c, "k_raycast_fine_2", st);
     if (c->depth == 11)
-        k_raycast_fine_2<11><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
+        k_raycast_fine_2<11><<<grid, kRayBlock, 0, st>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
     else
-        k_raycast_fine_2<14><<<grid, kRayBlock, 0, c->stream>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
+        k_raycast_fine_2<14><<<grid, kRayBlock, 0, st>>>(screen, back, oct, root, res_x, res_y, gx, gy, add_x, add_y, cam);
 }
 
 // snapshot source: `snap_src` if the caller knows a buffer with the same content (fused frame: the cache copy),
@@ -1043,6 +1044,36 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     c->last_slot = dst_slot;
     c->have_frame = true;
     c->last_idbuf = idbuffer;
+}
+
+// A batch of full raycasts (BASELINE.json config 5: many cameras, one scene).  Camera i is traced into buffer 0 (i even) or
+// buffer 2 (i odd) on two alternating streams, so the tail of one camera's kernel -- a few long rays on an almost idle GPU
+// -- overlaps the bulk of the next.  Asynchronous; svo_end_all_kernels() waits.  After the batch buffers 0 / 2 hold the
+// last even / odd camera's hit words and positions.
+extern "C" void svo_raycast_batch(svo_mem_t screenbuffer, svo_mem_t backbuffer, svo_mem_t octree, uint32_t octree_root,
+                                  int res_x, int res_y, int ncams, const svo_frame_params *cams)
+{
+    svo_ctx_t c = need_ctx();
+    if (!c) return;
+    if (!screenbuffer || !backbuffer || !octree || !cams || ncams < 0 || res_x <= 0 || res_y <= 0) { svo_fail(-39, "svo_raycast_batch: bad arguments"); return; }
+    const size_t n = (size_t)res_x * res_y;
+    if (n * 12 > screenbuffer->bytes || n * 48 > backbuffer->bytes) { svo_fail(-61, "svo_raycast_batch: buffers too small for %dx%d", res_x, res_y); return; }
+    flush_patches(c);                                                      // the buffers change hands
+    uint32_t *screen = (uint32_t *)screenbuffer->dptr;
+    float *back = (float *)backbuffer->dptr;
+    CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));                 // the alternate stream: behind the main stream so far
+    CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_frame_done, 0));
+    for (int i = 0; i < ncams; ++i) {
+        const svo_frame_params &p = cams[i];
+        const RayCam rc = make_ray_cam(p.v0, p.cols[0], p.cols[1], p.cols[2], p.fovx, p.fovy);
+        const int slot = (i & 1) ? 2 : 0;
+        do_fine_2(c, screen + (size_t)slot * n, back + (size_t)slot * n * 4, (const uint32_t *)octree->dptr, octree_root, res_x, res_y,
+                  res_x, res_y, 0, 0, rc, (i & 1) ? c->stream4 : c->stream);
+    }
+    if (ncams > 1) {                                                       // what follows on the main stream follows the whole batch
+        CU_CHECK(cudaEventRecord(c->ev_gather_done, c->stream4));
+        CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_gather_done, 0));
+    }
 }
 
 extern "C" int svo_frame_last_slot(void) { return g_ctx ? g_ctx->last_slot : 0; }

@@ -69,6 +69,7 @@ _svo_end_all = _sig("svo_end_all_kernels", None)
 _svo_round_up = _sig("svo_round_up", _sz, _i, _i)
 _svo_launch_count = _sig("svo_launch_count", C.c_uint64)
 _svo_frame_fused = _sig("svo_frame_fused", None, _vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(FrameParams))
+_svo_raycast_batch = _sig("svo_raycast_batch", None, _vp, _vp, _vp, _u32, _i, _i, _i, C.POINTER(FrameParams))
 _svo_frame_idbuf_size = _sig("svo_frame_idbuf_size", _i)
 _svo_frame_last_slot = _sig("svo_frame_last_slot", _i)
 _svo_frame_deferred_count = _sig("svo_frame_deferred_count", C.c_uint64)
@@ -247,6 +248,13 @@ def ocl_round_up(group_size, global_size):
 def frame_fused(screen, back, idbuf, octree, root, tex, params):
     _svo_frame_fused(screen.handle, back.handle, idbuf.handle, octree.handle, root, tex.handle if tex else None,
                      C.byref(params))
+    _check()
+
+
+def raycast_batch(screen, back, octree, root, res_x, res_y, params_list):
+    """Full raycasts of many cameras (svo_raycast_batch): camera i -> buffer 0 / 2 for even / odd i, consecutive cameras overlap."""
+    arr = (FrameParams * len(params_list))(*params_list)
+    _svo_raycast_batch(screen.handle, back.handle, octree.handle, root, res_x, res_y, len(params_list), arr)
     _check()
 
 

@@ -317,6 +317,15 @@ def full_raycast_enqueue(res_x, res_y):
     ocl.ocl_end()
 
 
+def full_raycast_batch(res_x, res_y, poses):
+    """Full raycasts for a list of (pos, rot) cameras through svo_raycast_batch; asynchronous (view-parallel batches)."""
+    plist = []
+    for pos, rot in poses:
+        set_camera(pos, rot)
+        plist.append(prepare_params(res_x, res_y, 0))
+    ocl.raycast_batch(S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree, S.octree_root_normal, res_x, res_y, plist)
+
+
 def idbuf_size():
     return ocl.frame_idbuf_size() if S.mode in ("fused", "pingpong") else S.idbuf_size
 

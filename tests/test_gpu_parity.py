@@ -405,6 +405,32 @@ def test_cache_rotation_reference_mode(svo, orc, world):
         svo.ocl_init(0)
 
 
+def test_raycast_batch(svo, orc, world):
+    """svo_raycast_batch (BASELINE config 5): five cameras traced back to back into buffers 0 / 2 on two alternating streams;
+    afterwards the buffers hold the last even / odd camera's full raycast, bit for bit the oracle's raycast_fine_2."""
+    octree, root = world
+    rx, ry = 320, 192
+    n = rx * ry
+    rc = svo.raycast
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused")
+    try:
+        poses = [((10 + 0.9 * f, 22 + 0.3 * f, 9 + 0.7 * f), (0.4 + 0.01 * f, 0.7 + 0.05 * f, 0.0)) for f in range(5)]
+        rc.full_raycast_batch(rx, ry, poses)
+        screen, back, _ = rc.read_buffers(rx, ry)
+        for slot, f in ((0, 4), (2, 3)):
+            cam = ofr.camera_args(*poses[f])
+            es = np.full(4 * n, HOLE, dtype=np.uint32)
+            eb = np.zeros(16 * n, dtype=np.float32)
+            orc.raycast_fine_2(es, eb, octree, root, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], gx=rx, gy=ry, threads=4)
+            assert np.array_equal(screen[slot * n:(slot + 1) * n], es[:n]), f"slot {slot}"
+            got = back[slot * 4 * n:(slot + 1) * 4 * n].view(np.uint32).reshape(n, 4)[:, :3]
+            assert np.array_equal(got, eb[:4 * n].view(np.uint32).reshape(n, 4)[:, :3]), f"slot {slot} xyz"
+    finally:
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
 def test_golden_frames(svo):
     """The CUDA path against the committed vectors produced by the reference's own source (tests/golden)."""
     from golden.make_golden import golden_pose, NFRAMES
