@@ -558,7 +558,7 @@ def main():
                "k_proj_scatter2": (40.0 * n if args.mode == "fused" else 4.0 * nsrc_px + 16.0 * V) + 8.0 * V,   # + one 8-byte key RMW each
                # keys in, gather, dest out, hole words, re-arm, ids, colorized word per pixel
                "k_resolve_gather": 8.0 * n + 20.0 * W + 20.0 * W + 4.0 * (n - W) + 8.0 * W + 4.0 * H + 4.0 * n,
-               "k_resolve_ids": 8.0 * n + 4.0 * H,                                 # keys in, ids out
+               "k_hole_ids": 8.0 * n + 4.0 * H,                                 # keys in, ids out
                "k_rays_tile": (4.0 * L + 16.0) * tile_rays, "k_rays_holes": (4.0 * L + 20.0) * H,
                "k_copy_colorize": 40.0 * n,                                       # only when the host observes the buffers
                "k_fill_list": 28.0 * resid_px, "k_apply_patches": 12.0 * resid_px}

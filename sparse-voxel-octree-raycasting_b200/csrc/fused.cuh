@@ -185,13 +185,13 @@ struct GatherArgs {
 // (kernel.cl:571 against an empty destination).
 __device__ __forceinline__ bool key_valid(unsigned long long k) { return k != kKeyEmpty && (uint32_t)(k >> 32) < 0xffffff00u; }
 
-// MODE 0: everything in one launch.  The split form takes the hole index list off the frame's critical path:
-// MODE 1 (ids): keys -> hole cells -> scan -> id buffer only (reads 8 B/pixel, writes the list), so the hole rays can start
-//               a dozen microseconds after the reprojection;
-// MODE 2 (gather): re-arm + depth-test resolve + gather + destination / image / gap-filter list, running BESIDE the hole
-//               rays on another stream.  It writes nothing into the 2x2 cells the rays fill (MODE 0 stores hole words there
-//               that the rays then overwrite), so the two never touch the same word; no tickets, no scan.
-template <int MODE>
+// IDS = true: everything in one launch (hole ids included).  The split form takes the hole index list off the frame's
+// critical path: k_hole_ids (below) produces it from the keys alone, so the hole rays can start a dozen microseconds after
+// the reprojection, and this kernel with IDS = false -- re-arm + depth-test resolve + gather + destination / image /
+// gap-filter list -- runs BESIDE the hole rays on another stream.  It then writes nothing into the 2x2 cells the rays fill
+// (the one-launch form stores hole words there that the rays overwrite), so the two never touch the same word; no tickets,
+// no scan.
+template <bool IDS>
 __global__ void __launch_bounds__(256)
 k_resolve_gather(const GatherArgs a)
 {
@@ -205,15 +205,14 @@ k_resolve_gather(const GatherArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *__restrict__ dscreen = a.screen + a.dst0;
     float *__restrict__ dback = a.back + (size_t)a.dst0 * 4;
-    if (MODE != 2) {
+    if (IDS) {
         if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
         __syncthreads();
     }
-    const unsigned int ticket = MODE != 2 ? ticket_s : blockIdx.x;
-    if (MODE != 1 && ticket == 0 && tid == 0) a.next_resid_count[0] = 0;   // re-arm the counter used two frames from now
+    const unsigned int ticket = IDS ? ticket_s : blockIdx.x;
+    if (ticket == 0 && tid == 0) a.next_resid_count[0] = 0;   // re-arm the counter used two frames from now
 
     if (ticket >= (unsigned)ncta) {
-        if (MODE == 1) return;                                   // (never launched: the id pass has no strip CTAs)
         // pixels outside the whole 16x16 blocks (right / bottom strips when the resolution is not a multiple of 16):
         // resolve only, they never enter the hole gather (kernel.cl:243-244)
         const int strip_cta = (int)ticket - ncta;
@@ -292,9 +291,9 @@ k_resolve_gather(const GatherArgs a)
         }
         const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
         const unsigned long long tag = (unsigned long long)a.epoch << 34;
-        if (MODE != 2 && tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+        if (IDS && tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
 
-        if (MODE != 1 && active) {
+        if (active) {
             // all four gathers in flight before the first use
             uint32_t col[4]; float4 pc[4];
 #pragma unroll
@@ -312,7 +311,7 @@ k_resolve_gather(const GatherArgs a)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (staged && inr[i] && !(MODE == 2 && hole)) {
+                if (staged && inr[i] && !(!IDS && hole)) {
                     const size_t q = pp[i >> 1] + (i & 1);
                     scol[i] = ld_stream(a.stage_s + q);
                     spc[i] = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + q * 4));      // w unused
@@ -336,13 +335,13 @@ k_resolve_gather(const GatherArgs a)
                         if (inr[i]) dback[(p + j) * 4 + 3] = phz;                 // the tile ray supplies colour and xyz, never w
                         else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
                     }
-                    if (staged && inr[i] && !(MODE == 2 && hole)) {               // ... from the staging buffers
+                    if (staged && inr[i] && !(!IDS && hole)) {               // ... from the staging buffers
                         out[j] = scol[i];
                         *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc[i].x, spc[i].y);
                         dback[(p + j) * 4 + 2] = spc[i].z;
                     }
                 }
-                if (MODE == 2 && hole) continue;                              // the hole rays own this cell
+                if (!IDS && hole) continue;                              // the hole rays own this cell
                 const bool w0 = !inr[2 * r] || staged, w1 = !inr[2 * r + 1] || staged;
                 if (even && w0 && w1) {
                     *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
@@ -356,7 +355,7 @@ k_resolve_gather(const GatherArgs a)
         // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416); slots are reserved with one
         // global atomic per CTA (a single counter hit by every pixel would serialise in L2)
         unsigned int rflags = 0;
-        if (MODE != 1 && active && !hole) {
+        if (active && !hole) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int px = x + (i & 1), py = y + (i >> 1);
@@ -367,9 +366,9 @@ k_resolve_gather(const GatherArgs a)
         unsigned int rofs = 0;
         if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
         __syncthreads();
-        if (MODE != 1 && tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
+        if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
         // decoupled look-back over the predecessors' aggregates (ticket order)
-        if (MODE != 2 && warp == 0) {
+        if (IDS && warp == 0) {
             uint32_t excl = 0;
             if (ticket > 0) {
                 int look = (int)ticket - 1;
@@ -400,8 +399,8 @@ k_resolve_gather(const GatherArgs a)
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
         }
-        const uint32_t cta_prefix = MODE != 2 ? cta_prefix_s : 0u;
-        if (MODE != 2 && active) {
+        const uint32_t cta_prefix = IDS ? cta_prefix_s : 0u;
+        if (IDS && active) {
             const uint32_t ofs = cta_prefix + before_me;
             if ((warp & 1) == 0 && lane == 0) {
                 if (b > 0) a.idb[b] = my_block_cnt;                         // raycast_counthole :273 (word 0 becomes the total)
@@ -415,15 +414,131 @@ k_resolve_gather(const GatherArgs a)
                 o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
             }
         }
-        if (MODE != 2 && ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
+        if (IDS && ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
     }
-    if (MODE == 2) return;
+    if (!IDS) return;
     // the last CTA to finish re-arms the ticket counters for the next frame
     __syncthreads();
     if (tid == 0) {
         __threadfence();
         const unsigned int done = atomicAdd(&a.s.counters[1], 1u);
         if (done == gridDim.x - 1) { a.s.counters[0] = 0; a.s.counters[1] = 0; __threadfence(); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The hole index list alone (raycast_counthole / sumids / writeids, kernel.cl:234-340) from the reprojection keys: what the
+// hole rays wait for.  Same layout of work as k_resolve_gather -- one thread per 2x2 cell, a warp pair per 16x16 block, warp
+// ballots, decoupled look-back over CTAs in ticket order -- but every CTA takes kIdsBlocksPerCta = 8 blocks (two cells per
+// thread, all 64 B of keys in flight at once), so the 7 680 blocks of a 1920x1024 frame are one wave of 960 CTAs with one
+// ticket and one look-back each.  Reads 8 B/pixel, writes the list.
+constexpr int kIdsBlocksPerCta = 2 * kGatherBlocksPerCta;
+
+__global__ void __launch_bounds__(256)
+k_hole_ids(const unsigned long long *__restrict__ key, uint32_t *__restrict__ idb, FusedScratch s, uint32_t epoch, int res_x, int res_y)
+{
+    __shared__ unsigned int ticket_s;
+    __shared__ uint32_t warp_cnt[2][8];
+    __shared__ uint32_t cta_prefix_s;
+    const int nbx = res_x / 16, nby = res_y / 16, nblocks = nbx * nby;
+    const int ncta = (nblocks + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) ticket_s = atomicAdd(&s.counters[0], 1u);
+    __syncthreads();
+    const unsigned int ticket = ticket_s;
+    const bool even = (res_x & 1) == 0;
+    bool hole[2] = {false, false}, active[2];
+    int x[2] = {0, 0}, y[2] = {0, 0}, blk[2];
+    unsigned long long k[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {                                      // iteration c covers blocks ticket*8 + c*4 .. +3
+        blk[c] = (int)ticket * kIdsBlocksPerCta + c * kGatherBlocksPerCta + (warp >> 1);
+        active[c] = blk[c] < nblocks;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) k[c][i] = kKeyEmpty;
+        if (active[c]) {
+            const int bx = blk[c] % nbx, by = blk[c] / nbx;
+            x[c] = bx * 16 + (lane & 7) * 2;
+            y[c] = by * 16 + ((warp & 1) * 4 + (lane >> 3)) * 2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const size_t p = (size_t)(y[c] + r) * res_x + x[c];
+                if (even) {
+                    const ulonglong2 kk = ld_stream(reinterpret_cast<const ulonglong2 *>(key + p));
+                    k[c][2 * r] = kk.x; k[c][2 * r + 1] = kk.y;
+                } else { k[c][2 * r] = ld_stream(key + p); k[c][2 * r + 1] = ld_stream(key + p + 1); }
+            }
+        }
+    }
+    unsigned m[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        hole[c] = active[c] && !key_valid(k[c][0]) && !key_valid(k[c][1]) && !key_valid(k[c][2]) && !key_valid(k[c][3]);
+        m[c] = __ballot_sync(0xffffffffu, hole[c]);
+        if (lane == 0) warp_cnt[c][warp] = 4u * (uint32_t)__popc(m[c]);
+    }
+    __syncthreads();
+    uint32_t cta_total = 0, before_me[2] = {0, 0}, my_cnt[2];
+#pragma unroll
+    for (int j = 0; j < kIdsBlocksPerCta; ++j) {                       // block j of this CTA: iteration j / 4, warp pair j % 4
+        const uint32_t cnt = warp_cnt[j / kGatherBlocksPerCta][2 * (j % kGatherBlocksPerCta)] + warp_cnt[j / kGatherBlocksPerCta][2 * (j % kGatherBlocksPerCta) + 1];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) if (j < c * kGatherBlocksPerCta + (warp >> 1)) before_me[c] += cnt;
+        cta_total += cnt;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) my_cnt[c] = warp_cnt[c][warp & ~1] + warp_cnt[c][warp | 1];
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    if (tid == 0) atomicExch(&s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+    if (warp == 0) {                                                   // decoupled look-back over the predecessors' aggregates
+        uint32_t excl = 0;
+        if (ticket > 0) {
+            int look = (int)ticket - 1;
+            while (true) {
+                const int idx = look - lane;                           // each lane inspects one predecessor
+                unsigned long long v = 0;
+                if (idx >= 0) {
+                    do { v = *reinterpret_cast<volatile unsigned long long *>(&s.scan_state[idx]); }
+                    while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0);
+                }
+                const bool is_prefix = idx >= 0 && ((v >> 32) & 3ull) == 2ull;
+                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;             // sum up to and including the first inclusive prefix
+                uint32_t val = (idx >= 0 && lane <= first) ? (uint32_t)v : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                excl += val;
+                if (pm || look - 32 < 0) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(&s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
+        }
+        if (lane == 0) cta_prefix_s = excl;
+    }
+    __syncthreads();
+    const uint32_t cta_prefix = cta_prefix_s;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (!active[c]) continue;
+        const uint32_t ofs = cta_prefix + before_me[c];
+        if ((warp & 1) == 0 && lane == 0) {
+            if (blk[c] > 0) idb[blk[c]] = my_cnt[c];                   // raycast_counthole :273 (word 0 becomes the total)
+            idb[nblocks + blk[c]] = ofs;                               // raycast_sumids :292
+        }
+        if (hole[c]) {
+            const uint32_t first_half = warp_cnt[c][warp & ~1];
+            const uint32_t rank = (uint32_t)__popc(m[c] & ((1u << lane) - 1u));
+            uint32_t *o = idb + 2 * (uint32_t)nblocks + ofs + ((warp & 1) ? first_half : 0u) + 4u * rank;
+            const uint32_t val = (uint32_t)x[c] | ((uint32_t)y[c] << 16);  // raycast_writeids :324,:334-337
+            o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
+        }
+    }
+    if (ticket == (unsigned)ncta - 1 && tid == 0) idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
+    __syncthreads();
+    if (tid == 0) {                                                    // the last CTA to finish re-arms the ticket counters
+        __threadfence();
+        const unsigned int done = atomicAdd(&s.counters[1], 1u);
+        if (done == gridDim.x - 1) { s.counters[0] = 0; s.counters[1] = 0; __threadfence(); }
     }
 }
 

@@ -916,9 +916,9 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (pingpong) do_memset(c, screen, 0, kHole, n * 4);
         else do_memset(c, screen, n, kHole, n * 3);
     }
-    // Split resolve (default): the hole index list first (k_resolve_gather<1>, keys only), so the hole rays -- the longest
+    // Split resolve (default): the hole index list first (k_hole_ids, keys only), so the hole rays -- the longest
     // link of the frame's critical chain -- start a dozen microseconds after the reprojection; the resolve/gather pass
-    // proper (<2>) runs beside them on the fourth stream and never writes the cells the rays fill.  The tile rays then
+    // proper runs beside them on the fourth stream and never writes the cells the rays fill.  The tile rays then
     // write into staging buffers (they depend on nothing but the camera, so they start with the frame, beside the
     // reprojection, instead of beside the hole rays) and the gather pass moves their pixels into the destination.
     static const bool split_resolve = !getenv("SVO_NO_SPLIT_RESOLVE");
@@ -983,8 +983,8 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
                            staged ? c->stage_s : nullptr, staged ? c->stage_b : nullptr};
     if (split) {
         {   // :272-315 hole gather from the keys alone, ids in the reference's order, idb[0] = idbuf_size
-            LAUNCH(c, "k_resolve_ids");
-            k_resolve_gather<1><<<(unsigned)ncta, 256, 0, c->stream>>>(ga);
+            LAUNCH(c, "k_hole_ids");
+            k_hole_ids<<<(unsigned)((nb + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta), 256, 0, c->stream>>>(c->key, idb, fs, c->epoch, res_x, res_y);
         }
         CU_CHECK(cudaEventRecord(c->ev_ids_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_ids_done, 0));                             // (re-arms the keys the id pass reads)
@@ -992,13 +992,13 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (staged) CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_tile_done, 0));                // (moves the tile rays' pixels over)
         {   // :157 clear + depth-test resolve + gather + image + gap-filter list
             LAUNCH_ON(c, "k_resolve_gather", c->stream4);
-            k_resolve_gather<2><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream4>>>(ga);
+            k_resolve_gather<false><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream4>>>(ga);
         }
         CU_CHECK(cudaEventRecord(c->ev_gather_done, c->stream4));
         join_fill();                                                                              // the hole rays write buffer 0 too
     } else {   // :157 clear + depth-test resolve + :272-315 hole gather in one launch
         LAUNCH(c, "k_resolve_gather");
-        k_resolve_gather<0><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
+        k_resolve_gather<true><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
     }
     {   // :332-359 hole rays, count on the device
         LAUNCH(c, "k_rays_holes");
