@@ -458,14 +458,16 @@ def main():
         rc.draw_prepared(P[f], sync=True)
     DEPTH = 3                                                        # frames in flight: render f, pack f-1, copy f-2
     host_frames = [ocl.host_alloc(n * 3) for _ in range(DEPTH)]
-    # PCIe warm-up: the link idles at a low speed and takes tens of ms of traffic to train up; a timed loop that starts cold
-    # measured 1 700-2 000 frames/s in one run out of five.  64 untimed read-backs of the last warm-up frame.
-    for i in range(64):
+    # PCIe warm-up: the link idles at a low speed and takes a while under traffic to train up; a timed loop that starts cold
+    # measured anything between 1 700 and 6 400 frames/s.  0.3 s of untimed read-backs of the last warm-up frame.
+    t_w, i = time.perf_counter(), 0
+    while i < 64 or (time.perf_counter() - t_w < 0.3 and i < 4096):
         ocl.present_rgb24_async(host_frames[i % DEPTH], rc.S.mem_screenbuffer_tex, n, i % DEPTH)
         if i >= DEPTH - 1:
             ocl.present_wait((i - (DEPTH - 1)) % DEPTH)
-    for i in range(64 - (DEPTH - 1), 64):
-        ocl.present_wait(i % DEPTH)
+        i += 1
+    for j in range(i - (DEPTH - 1), i):
+        ocl.present_wait(j % DEPTH)
     sync_all()
     t0 = time.perf_counter()
     for f in range(args.warmup, total):
