@@ -453,39 +453,43 @@ def main():
     del scr_all
 
     # ---- e2e: same frames again (fresh cache state), each finished frame read back into pinned host memory ----
-    rc.reset_frames()
-    for f in range(args.warmup):
-        rc.draw_prepared(P[f], sync=True)
     DEPTH = 3                                                        # frames in flight: render f, pack f-1, copy f-2
     host_frames = [ocl.host_alloc(n * 3) for _ in range(DEPTH)]
-    # PCIe warm-up: the link idles at a low speed and takes a while under traffic to train up; a timed loop that starts cold
-    # measured anything between 1 700 and 6 400 frames/s.  0.3 s of untimed read-backs of the last warm-up frame.
-    t_w, i = time.perf_counter(), 0
-    while i < 64 or (time.perf_counter() - t_w < 0.3 and i < 4096):
-        ocl.present_rgb24_async(host_frames[i % DEPTH], rc.S.mem_screenbuffer_tex, n, i % DEPTH)
-        if i >= DEPTH - 1:
-            ocl.present_wait((i - (DEPTH - 1)) % DEPTH)
-        i += 1
-    for j in range(i - (DEPTH - 1), i):
-        ocl.present_wait(j % DEPTH)
-    sync_all()
-    t0 = time.perf_counter()
-    for f in range(args.warmup, total):
-        # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame as R,G,B
-        # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frames render.  The
-        # caller owns frame f-2 after its present_wait.
-        k = rc.draw_present(P[f], host_frames, rgb24=True)
-        if f - (DEPTH - 1) >= args.warmup:
-            ocl.present_wait((f - (DEPTH - 1)) % DEPTH)
-    for f in range(max(args.warmup, total - (DEPTH - 1)), total):
-        ocl.present_wait(f % DEPTH)
-    e2e_s = time.perf_counter() - t0
+    rc.prepare_present(DEPTH)                                        # no allocation inside the timed loop
+    E2E_PASSES = 3        # the loop waits on the host every frame and is sensitive to whatever else the box does: median of three passes
+    e2e_pass_s = []
+    for e2e_pass in range(E2E_PASSES):
+        rc.reset_frames()
+        for f in range(args.warmup):
+            rc.draw_prepared(P[f], sync=True)
+        if e2e_pass == 0:
+            # PCIe warm-up: 0.3 s of untimed read-backs of the last warm-up frame through every slot (link training, staging
+            # buffers, first-touch of the pinned pages all happen here, not in the timed loop)
+            t_w, i = time.perf_counter(), 0
+            while i < 64 or (time.perf_counter() - t_w < 0.3 and i < 4096):
+                ocl.present_rgb24_async(host_frames[i % DEPTH], rc.S.present_tex[i % DEPTH], n, i % DEPTH)
+                if i >= DEPTH - 1:
+                    ocl.present_wait((i - (DEPTH - 1)) % DEPTH)
+                i += 1
+            for j in range(i - (DEPTH - 1), i):
+                ocl.present_wait(j % DEPTH)
+        sync_all()
+        t0 = time.perf_counter()
+        for f in range(args.warmup, total):
+            # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame as R,G,B
+            # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frames render.  The
+            # caller owns frame f-2 after its present_wait.
+            k = rc.draw_present(P[f], host_frames, rgb24=True)
+            if f - (DEPTH - 1) >= args.warmup:
+                ocl.present_wait((f - (DEPTH - 1)) % DEPTH)
+        for f in range(max(args.warmup, total - (DEPTH - 1)), total):
+            ocl.present_wait(f % DEPTH)
+        e2e_pass_s.append(time.perf_counter() - t0)
     host_frame = host_frames[k]
     sampler.stop_flag = True
     sampler.join()
     checksum = int(np.frombuffer(host_frame, dtype=np.uint8, count=n * 3).sum(dtype=np.uint64))
-    # the box's plain device -> pinned-host copy rate, to read the e2e figure against (it moves n*3 bytes per frame over this link;
-    # measured: 35-50 GB/s on most boxes of the pool, ~12 GB/s on some, where e2e then sits at ~2 000 frames/s whatever the GPU does)
+    # the box's plain device -> pinned-host copy rate, to read the e2e figure against (it moves n*3 bytes per frame over this link)
     try:
         dsrc = torch.empty(64 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
         hdst = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
@@ -533,12 +537,13 @@ def main():
     sync_all()
 
     # ---- max over ranks ----
-    t = torch.tensor([ms, e2e_s * 1000.0, cams_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t = torch.tensor([ms, 0.0, cams_ms] + [x * 1000.0 for x in e2e_pass_s], dtype=torch.float64, device=f"cuda:{local_rank}")
     mr = torch.tensor([mrays], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(mr, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, cams_ms_max = float(t[0]), float(t[1]), float(t[2])
+    e2e_passes_ms = sorted(float(v) for v in t[3:])                  # per pass: max over ranks
+    ms_max, e2e_ms_max, cams_ms_max = float(t[0]), e2e_passes_ms[len(e2e_passes_ms) // 2], float(t[2])
     fps = world * args.steps / (ms_max * 1e-3)
     e2e_fps = world * args.steps / (e2e_ms_max * 1e-3)
 
@@ -579,6 +584,7 @@ def main():
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus,
+                        "passes_fps": [round(world * args.steps / (v * 1e-3), 1) for v in e2e_passes_ms], "value_is": "median of the passes",
                         "d2h_link_gbs": d2h_gbs, "d2h_used_gbs": e2e_fps / world * n * 3 / 1e9},
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},

@@ -247,6 +247,14 @@ def draw_prepared(p, sync=True):
         ocl.ocl_end_all_kernels()
 
 
+def prepare_present(depth):
+    """Allocate the colorize targets draw_present() rotates through (one per frame in flight) ahead of time: a cudaMalloc
+    inside a frame loop stalls it for anything between 0.1 and 100 ms."""
+    while len(S.present_tex) < depth:
+        S.present_tex.append(S.mem_screenbuffer_tex if not S.present_tex else ocl.ocl_malloc(S.mem_screenbuffer_tex.size))
+    S.mem_screenbuffer_tex2 = S.present_tex[1] if depth > 1 else None
+
+
 def draw_present(p, host_frames, rgb24=False):
     """Pipelined headless frame: with D = len(host_frames) (2..4) buffers, frame p.frame is rendered into colorize target
     k = p.frame % D and its read-back into host_frames[k] (page-locked, ocl.host_alloc) is queued on the copy stream, so
@@ -254,9 +262,7 @@ def draw_present(p, host_frames, rgb24=False):
     before frame p.frame + D is issued.  rgb24: the frame arrives as R,G,B bytes (PPM payload, 3 bytes per pixel) instead
     of the PBO's 0x00RRGGBB words."""
     depth = len(host_frames)
-    while len(S.present_tex) < depth:                    # one colorize target per frame in flight
-        S.present_tex.append(S.mem_screenbuffer_tex if not S.present_tex else ocl.ocl_malloc(S.mem_screenbuffer_tex.size))
-    S.mem_screenbuffer_tex2 = S.present_tex[1] if depth > 1 else None
+    prepare_present(depth)
     k = p.frame % depth
     tex = S.present_tex[k]
     S.frame = p.frame
