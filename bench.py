@@ -156,6 +156,31 @@ def measured_peak():
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own kernel.cl through oracle/_ref (or the C restatement) on the host cores
 # --------------------------------------------------------------------------------------------------------------
+def opencl_probe():
+    """north_star asks for the reference kernel.cl on the host through a CPU OpenCL runtime (PoCL).  This image has none (SURVEY
+    F3); the box is re-probed at run time so that the report says what it found: platform names, or why there are none."""
+    import ctypes
+    try:
+        cl = ctypes.CDLL("libOpenCL.so.1")
+    except OSError:
+        return "no libOpenCL.so.1"
+    try:
+        n = ctypes.c_uint(0)
+        rc_ = cl.clGetPlatformIDs(0, None, ctypes.byref(n))
+        if rc_ != 0 or n.value == 0:
+            return f"ICD loader present, 0 platforms (clGetPlatformIDs -> {rc_})"
+        ids = (ctypes.c_void_p * n.value)()
+        cl.clGetPlatformIDs(n.value, ids, None)
+        names = []
+        for pid in ids:
+            buf = ctypes.create_string_buffer(256)
+            cl.clGetPlatformInfo(ctypes.c_void_p(pid), 0x0902, 256, buf, None)      # CL_PLATFORM_NAME
+            names.append(buf.value.decode(errors="replace"))
+        return "platforms: " + ", ".join(names) + " (not used: the baseline runs kernel.cl through the C++ shim, oracle/_ref)"
+    except Exception as e:                                                          # a broken ICD must not take the bench down
+        return f"probe failed: {type(e).__name__}"
+
+
 def cpu_arm(octree, root, steps, warmup, budget_s):
     """Runs frames 0.. of the same flythrough at 1920x1024 on the host; fps over the frames after `warmup`."""
     from oracle import binding, frame as ofr
@@ -180,7 +205,7 @@ def cpu_arm(octree, root, steps, warmup, budget_s):
             break
     fps = len(times) / sum(times)
     return dict(value=fps, unit="frames/s", cores=cores, kind=kind, frames_timed=len(times),
-                ms_per_step=1000.0 * sum(times) / len(times), full_raycast_mrays_per_s=rays_full,
+                ms_per_step=1000.0 * sum(times) / len(times), full_raycast_mrays_per_s=rays_full, opencl_cpu_runtime=opencl_probe(),
                 sample=f"frames {warmup}..{warmup + len(times) - 1} of the same 1920x1024 flythrough (frames 0..{warmup - 1} untimed warm-up), "
                        f"{'reference kernel.cl via oracle/_ref' if kind == 'reference' else 'C restatement oracle/svo_oracle.c'}, "
                        f"OpenMP over work-groups for the race-free kernels, raycast_proj/sumids/fillhole2 serial")
@@ -384,7 +409,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
                 "config": {"workload": workload_name(scene_name)},
                 "full_raycast_mrays_per_s": r["full_raycast_mrays_per_s"],
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "opencl_cpu_runtime")},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -601,7 +626,7 @@ def main():
                                           "traffic": ncu_traffic(sk), "algorithmic_bytes_per_launch": alg[sk], "avg_launch_ms": s_ms}
         if not args.no_cpu_baseline and world == 1:
             r = cpu_arm(octree, root, steps=24, warmup=args.warmup, budget_s=25.0)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "opencl_cpu_runtime")}
             line["cpu_baseline"]["full_raycast_mrays_per_s"] = r["full_raycast_mrays_per_s"]
     rc.raycast_exit()
     extras = {}
