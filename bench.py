@@ -624,6 +624,12 @@ def main():
             s_ach = alg[sk] / (s_ms * 1e-3) / 1e9
             line["roofline_streaming"] = {"kernel": sk, "bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
                                           "traffic": ncu_traffic(sk), "algorithmic_bytes_per_launch": alg[sk], "avg_launch_ms": s_ms}
+        # and for the other half of the metric, the full-screen traversal kernel (issue bound: DESIGN.md section 4)
+        fr_bytes = (4.0 * L + 16.0) * n
+        fr_ach = fr_bytes / (float(np.median(ray_ms)) * 1e-3) / 1e9
+        line["roofline_full_raycast"] = {"kernel": "k_raycast_fine_2", "bound": "hbm", "achieved": fr_ach, "peak": peak, "unit": "GB/s", "frac": fr_ach / peak,
+                                         "traffic": ncu_traffic("k_raycast_fine_2"), "algorithmic_bytes_per_launch": fr_bytes,
+                                         "avg_launch_ms": float(np.median(ray_ms)), "note": "instruction-issue bound (ncu: issue slots 83 % busy, 21 of 32 lanes active); HBM is 1 % busy"}
         if not args.no_cpu_baseline and world == 1:
             r = cpu_arm(octree, root, steps=24, warmup=args.warmup, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "opencl_cpu_runtime")}
