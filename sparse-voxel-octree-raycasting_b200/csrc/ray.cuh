@@ -15,6 +15,13 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// measurement hooks of tools/ubench/raylat.cu (loop trips, descents and cycles per ray); they expand to nothing in the library
+#ifndef SVO_TRIP_HOOK
+#define SVO_TRIP_HOOK(what)
+#define SVO_TRIP_DECL
+#define SVO_TRIP_END
+#endif
+
 namespace svo {
 
 constexpr uint32_t kHole = 0xffffff00u;       // kernel/kernel.cl:267
@@ -184,6 +191,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     constexpr uint32_t kLevel = (uint32_t)STRIDE * 4u;                // bytes between two levels of one thread's column
     sts_u32(sbase + D * kLevel, root);
     sts_u32(sbase + (D + 1) * kLevel, root);
+    SVO_TRIP_DECL
 
     // The reference's loop takes one of two branches per iteration (descend into an occupied child / step through an
     // empty cell).  Same per-ray sequence, arranged "while-while": the lanes of a warp first run their descents together,
@@ -192,6 +200,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     // exactly as in the reference.)
     for (;;) {
         int cx, cy, cz;
+        SVO_TRIP_HOOK(0)
         for (;;) {                                                     // descend while the child under the ray is occupied
             cx = ix >> rekursion; cy = iy >> rekursion; cz = iz >> rekursion;
             const int node_index = ((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) ^ sign_xyz;
@@ -199,6 +208,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
             if (!node_test) break;
             nodeid = fetch_child<STRAIGHT>(oct, nodeid, rekursion == kBlockRootLevel, local_root, (uint32_t)node_index, node_test, rekursion);
             if (rekursion <= lod) { hit = true; break; }               // :172
+            SVO_TRIP_HOOK(1)
             --rekursion;
             sts_u32(sbase + (uint32_t)rekursion * kLevel, nodeid);
         }
@@ -229,6 +239,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
         if ((x0ry & kScaleMax) != 0) break;                            // :211 the ray left the world through y
     }
 
+    SVO_TRIP_END
     if (sign_xyz & 1) px = (float)kScaleMax - px;
     if (sign_xyz & 2) py = (float)kScaleMax - py;
     if (sign_xyz & 4) pz = (float)kScaleMax - pz;
