@@ -7,8 +7,11 @@ copy, small-gap filter, colorize), reported as frames/s, plus the full-raycast p
 
 One JSON line on stdout (rank 0).  A "step" is one frame.  Keys beyond the base contract:
   full_raycast_mrays_per_s   primary rays/s of a full-screen raycast (config 1 of BASELINE.json)
-  roofline                   dominant kernel of the warped frame vs the measured HBM peak
-  cpu_baseline               the reference's own kernel.cl (oracle/_ref) or its C restatement on the host cores
+  roofline                   dominant kernel of the warped frame (traversal kernels: issue roof, not HBM) ; roofline_frame: the
+                             whole frame's SURVEY 8(d) bytes against the measured HBM peak
+  cpu_baseline               the reference's own kernel.cl (oracle/_ref) or its C restatement on the host cores, every kernel
+                             work-group-parallel; cpu_baseline_fast_math: its -ffast-math twin (src/ocl.h:47)
+  parity                     GPU output compared bit for bit with the serial reference (oracle/_ref) on the measured configurations
   e2e                        the same frames through the C ABI with the finished frame read back to host memory
 Scene: data/Imrodh.rle4 if present, else the stand-in S1 (procedural, written as .rle4 and loaded through the
 .rle4 loader) -- the reference's only scene is not in the mount.
@@ -34,7 +37,9 @@ HOLE = 0xFFFFFF00
 
 def flythrough_pose(f, cam_id=0):
     """SURVEY.md 8(d) config 2: 20 world units/s at 60 fps forward-diagonal walk with a slow pan and pitch wobble;
-    cam_id offsets the start so that view-parallel ranks render different paths."""
+    cam_id offsets the start so that view-parallel ranks render different paths.  rot.x = +0.6 where the survey wrote -0.6:
+    with the reference's matrix conventions a negative pitch looks at the sky (98.5 % of the rays leave the world at once);
+    +0.6 looks down at the scene as the reference's screenshot does (oracle/frame.py:flythrough_pose is the same path)."""
     pos = (1.0 + f * 0.2357 + 13.0 * cam_id, 50.0, 1.0 + f * 0.2357 + 7.0 * cam_id)
     rot = (0.6 + 0.1 * math.sin(2.0 * math.pi * f / 128.0), 0.8 + 0.005 * f + 0.4 * cam_id, 0.0)
     return pos, rot
@@ -47,19 +52,23 @@ def scene_path():
     return os.path.join("/tmp", "svo_b200_standin_S1.rle4"), "stand-in S1 (procedural floor plate + 6 blobs, depth 11, via .rle4)"
 
 
-def make_scene(svo, path):
+def make_scene(path):
+    """The stand-in scene as a .rle4 file, written by the plain host program svo_make_scene (scene_io.cpp, no CUDA, not the
+    library) so that both arms read the same file and the reference arm never maps libsvo_b200.so."""
     if os.path.exists(path):
         return
-    vox = svo.scene.generate(kind=1, depth=11, size=0, nblobs=6, seed=0x5EED)
-    vox.write_rle4(path + ".tmp", 2048, 2048, 2048)
-    os.replace(path + ".tmp", path)
-    vox.free()
+    exe = os.path.join(ROOT, "sparse-voxel-octree-raycasting_b200", "svo_make_scene")
+    subprocess.run([exe, path], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
-def workload_name(scene_name):
-    """config.workload of both arms (b200 and --impl reference): BASELINE.json config 2."""
-    return (f"256-frame scripted flythrough, {RES_X}x{RES_Y}, full warping pipeline (reproject 2 buffers, 2x2 hole gather, hole raycast, "
-            f"8x4 tile refresh, cache copy, gap filter, colorize), scene: {scene_name}")
+def bench_config(scene_name, steps, warmup):
+    """config of BOTH arms (b200 and --impl reference), key for key: BASELINE.json config 2."""
+    return {"workload": f"scripted flythrough (SURVEY 8(d) config 2, 256 frames defined), {RES_X}x{RES_Y}, full warping pipeline (reproject 2 buffers, "
+                        f"2x2 hole gather, hole raycast, 8x4 tile refresh, cache copy, gap filter, colorize); frames {warmup}..{warmup + steps - 1} timed, "
+                        f"frames 0..{warmup - 1} warm-up (0 and 1 are full raycasts, src/raycast.h:150-154)",
+            "scene": scene_name, "resolution": f"{RES_X}x{RES_Y}", "timed_frames": [warmup, warmup + steps - 1],
+            "camera": "pos = (1,50,1) + f*(0.2357,0,0.2357), rot = (+0.6 + 0.1 sin(2 pi f/128), 0.8 + 0.005 f, 0)",
+            "l2": "no flush between frames: a frame reads what the previous one wrote, as in the real pipeline; the frame's buffers + octree (~140 MB) exceed the 126 MB L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -110,40 +119,77 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
-def pin_to_gpu_numa(index):
-    """Run this process on the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), so that the
-    page-locked frame buffers are allocated there and the per-frame read-back does not cross the socket interconnect.
-    Returns the CPU list used, or None (left alone) if anything about it cannot be determined."""
+def pin_to_gpu_numa(index, world=1):
+    """Run this process on the CPUs next to its GPU: the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function)
+    when that names a proper subset of the machine; otherwise (one-node boxes report every CPU for every GPU, which pins
+    nothing and leaves N ranks' launch threads to migrate over each other) the rank's own 1/world slice of the allowed CPUs.
+    Returns a description of the CPU set used, or None (left alone)."""
     try:
-        import pynvml as nv
-        nv.nvmlInit()
-        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:                   # NVML prints an 8-digit domain, sysfs a 4-digit one
-            bus = bus[4:]
-        txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
-        cpus = set()
-        for part in txt.split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus, how = None, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bus = bus.lower()
+            if len(bus.split(":")[0]) == 8:                   # NVML prints an 8-digit domain, sysfs a 4-digit one
+                bus = bus[4:]
+            txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+            loc = set()
+            for part in txt.split(","):
+                a, _, b = part.partition("-")
+                loc.update(range(int(a), int(b or a) + 1))
+            loc &= set(allowed)
+            if loc and len(loc) < len(allowed):
+                cpus, how = loc, f"numa {txt}"
+        except Exception:
+            pass
+        if cpus is None and world > 1 and len(allowed) >= 2 * world:
+            per = len(allowed) // world
+            cpus = set(allowed[index * per:(index + 1) * per])
+            how = f"slice {min(cpus)}-{max(cpus)} of {len(allowed)} cpus (no NUMA locality reported)"
         if not cpus:
             return None
         os.sched_setaffinity(0, cpus)
-        return txt
+        return how
     except Exception:
         return None
+
+
+def ncu_record(kernel):
+    """The committed ncu figures of `kernel` (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the --set full
+    capture of this same command): dram bytes, warp instructions, lanes per instruction, issue activity per launch."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))[kernel]
+    except Exception:
+        return {}
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this same
-    command (profiles/ncu_traffic.json, written by tools/dram_summary.py); None if there is none."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    try:
-        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`; None if there is no capture."""
+    v = ncu_record(kernel).get("dram_bytes_per_launch")
+    return float(v) if v is not None else None
+
+
+def issue_roofline(kernel, rays, launch_ms, sms, sm_mhz):
+    """Roof of a traversal kernel: it is bound by instruction issue (full screen) or by the dependent chain of its slowest
+    ray (sparse launches), not by HBM.  achieved = Mrays/s; peak = the rate at which the same instruction stream would
+    run with every issue slot of every SM sub-partition busy and all 32 lanes active: issue slots/s x 32 / thread
+    instructions per ray, from the committed ncu capture (warp instructions x lanes per instruction / rays)."""
+    rec = ncu_record(kernel)
+    achieved = rays / (launch_ms * 1e-3) / 1e6
+    out = {"kernel": kernel, "bound": "issue", "achieved": achieved, "unit": "Mrays/s", "avg_launch_ms": launch_ms, "rays_per_launch": rays,
+           "traffic": ncu_traffic(kernel), "issue_active_pct_ncu": rec.get("issue_active_pct"), "thr_per_inst_ncu": rec.get("thr_per_inst")}
+    if rec.get("warp_inst_per_launch") and rec.get("thr_per_inst") and (rec.get("rays_per_launch") or rays):
+        thread_inst_per_ray = rec["warp_inst_per_launch"] * rec["thr_per_inst"] / (rec.get("rays_per_launch") or rays)
+        peak = sms * 4 * sm_mhz * 1e6 * 32.0 / thread_inst_per_ray / 1e6
+        out.update(peak=peak, frac=achieved / peak, thread_inst_per_ray_ncu=thread_inst_per_ray,
+                   peak_is=f"{sms} SMs x 4 issue slots x {sm_mhz:.0f} MHz x 32 lanes / thread instructions per ray")
+    else:
+        out.update(peak=None, frac=None)
+    return out
 
 
 def measured_peak():
@@ -181,14 +227,24 @@ def opencl_probe():
         return f"probe failed: {type(e).__name__}"
 
 
-def cpu_arm(octree, root, steps, warmup, budget_s):
-    """Runs frames 0.. of the same flythrough at 1920x1024 on the host; fps over the frames after `warmup`."""
-    from oracle import binding, frame as ofr
+def oracle_octree(path, depth=11):
+    """(lib, kind, octree, root) of the CPU side, built by the CPU side's own loader: the reference's RLE4::load -> set_voxel ->
+    convert_tree_blocks when oracle/_ref exists (src/raycast.h:13-46), else the C restatement."""
+    from oracle import binding
     kind = "reference" if binding.have_ref() else "port"
-    orc = binding.get("ref" if kind == "reference" else "orc")
-    cores = orc.max_threads()
-    F = ofr.OracleFrame(orc, octree, root, RES_X, RES_Y, threads=cores)
-    times, rays_full = [], None
+    lib = binding.get("ref" if kind == "reference" else "orc")
+    octree, root = lib.build_octree_rle4(path)
+    return lib, kind, octree, root
+
+
+def cpu_arm(lib, kind, octree, root, steps, warmup, budget_s, threads=None):
+    """Frames 0.. of the same flythrough at 1920x1024 on the host cores; fps over the frames after `warmup`.  Every kernel runs
+    work-group-parallel on all host threads, the way an OpenCL CPU runtime runs the reference (raycast_proj with its payload
+    race: this leg feeds the clock, not the parity check)."""
+    from oracle import frame as ofr
+    cores = threads or lib.max_threads()
+    F = ofr.OracleFrame(lib, octree, root, RES_X, RES_Y, threads=cores, timed=True)
+    times = []
     t_start = time.perf_counter()
     f = 0
     while f < warmup + steps:
@@ -196,19 +252,94 @@ def cpu_arm(octree, root, steps, warmup, budget_s):
         t0 = time.perf_counter()
         F.draw(pos, rot)
         dt = time.perf_counter() - t0
-        if f == 0:
-            rays_full = (RES_X * RES_Y + RES_X * RES_Y // 32) / dt / 1e6      # frame 0 = every pixel + one tile, plus the warp passes
         if f >= warmup:
             times.append(dt)
         f += 1
         if budget_s and time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
     fps = len(times) / sum(times)
+    t_full = []
+    for _ in range(2):                                        # full-screen raycast_fine_2 (BASELINE.json config 1), second run timed
+        t0 = time.perf_counter()
+        oracle_full_raycast(lib, octree, root, RES_X, RES_Y, flythrough_pose(0))
+        t_full.append(time.perf_counter() - t0)
+    rays_full = RES_X * RES_Y / t_full[-1] / 1e6
+    what = {"reference": "reference kernel.cl via oracle/_ref", "port": "C restatement oracle/svo_oracle.c", "reference-fast-math": "reference kernel.cl via oracle/_ref built -O3 -ffast-math (mirrors -cl-fast-relaxed-math, src/ocl.h:47)"}[kind]
     return dict(value=fps, unit="frames/s", cores=cores, kind=kind, frames_timed=len(times),
                 ms_per_step=1000.0 * sum(times) / len(times), full_raycast_mrays_per_s=rays_full, opencl_cpu_runtime=opencl_probe(),
                 sample=f"frames {warmup}..{warmup + len(times) - 1} of the same 1920x1024 flythrough (frames 0..{warmup - 1} untimed warm-up), "
-                       f"{'reference kernel.cl via oracle/_ref' if kind == 'reference' else 'C restatement oracle/svo_oracle.c'}, "
-                       f"OpenMP over work-groups for the race-free kernels, raycast_proj/sumids/fillhole2 serial")
+                       f"{what}, OpenMP over work-groups for every kernel (raycast_proj with the reference's own atomics and payload race, "
+                       f"as an OpenCL CPU runtime would run it; sumids is one work item)")
+
+
+def cpu_arm_fast_math(octree, root, warmup, budget_s=12.0):
+    """The -ffast-math twin of the reference arm (the reference builds its kernels -cl-fast-relaxed-math, src/ocl.h:47);
+    None when oracle/_ref/libsvo_ref_fast.so was not built."""
+    from oracle import binding
+    if not binding.have_ref_fast():
+        return None
+    r = cpu_arm(binding.get("ref_fast"), "reference-fast-math", octree, root, 16, warmup, budget_s)
+    return {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "full_raycast_mrays_per_s")}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# parity of the measured configurations: GPU output against the serial reference, bit for bit
+# --------------------------------------------------------------------------------------------------------------
+def _mism(a, b):
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    if a.shape != b.shape:
+        return int(max(a.size, b.size))
+    return int(np.count_nonzero(a.view(np.uint32) != b.view(np.uint32)))
+
+
+def parity_flythrough(svo, lib, octree_cpu, root_cpu, params, nframes, mode):
+    """Frames 0..nframes-1 of the bench flythrough at 1920x1024: the colorized image, the hole index buffer and idbuf_size of
+    every frame, and after the last one every colour / coordinate buffer, GPU (fused frame, observed after each frame) against
+    the serial reference."""
+    from oracle import frame as ofr
+    rc = svo.raycast
+    n, nb = RES_X * RES_Y, (RES_X // 16) * (RES_Y // 16)
+    O = ofr.OracleFrame(lib, octree_cpu, root_cpu, RES_X, RES_Y, threads=lib.max_threads())
+    rc.reset_frames()
+    # the coordinate buffers still hold the timed passes' frames; pixels no kernel writes in this pass (stale positions under
+    # hole words, w of never-reprojected pixels) are compared too, so both sides start from zeroed memory
+    svo.ocl.ocl_memset(rc.S.mem_backbuffer, 0, 0, 16 * n * 4)
+    out = {"frames": nframes, "image_words": 0, "id_words": 0, "idbuf_size": 0, "buffer_words": 0, "position_words": 0, "hole_pixels": []}
+    for f in range(nframes):
+        O.draw(*flythrough_pose(f))
+        rc.draw_prepared(params[f], sync=True)
+        out["image_words"] += _mism(rc.read_frame(RES_X, RES_Y), O.tex)
+        gsz = rc.idbuf_size()
+        out["idbuf_size"] += int(gsz != O.idbuf_size)
+        out["hole_pixels"].append(int(O.idbuf_size))
+        idb = rc.S.mem_idbuffer.to_numpy(np.uint32, 2 * nb + max(gsz, O.idbuf_size))
+        out["id_words"] += _mism(idb[nb:2 * nb + O.idbuf_size], O.idbuf[nb:2 * nb + O.idbuf_size]) + _mism(idb[1:nb], O.idbuf[1:nb])
+    screen, back, _ = rc.read_buffers(RES_X, RES_Y)
+    if mode == "fused":                                   # exact mode: every buffer as the reference leaves it
+        out["buffer_words"] = _mism(screen, O.screen[:4 * n])
+        out["position_words"] = _mism(back, O.back[:16 * n])          # xyz and w of all four coordinate buffers, bit for bit
+    else:                                                 # ping-pong: the slot rendered into holds the reference's frame
+        slot = rc.last_slot()
+        out["buffer_words"] = _mism(screen[slot * n:(slot + 1) * n], O.screen[2 * n:3 * n])
+        g, o = back.reshape(4, n, 4)[slot], O.back[:16 * n].reshape(4, n, 4)[2]
+        valid = O.screen[2 * n:3 * n] != HOLE
+        out["position_words"] = int(np.count_nonzero((g[:, :3].view(np.uint32) != o[:, :3].view(np.uint32)) & valid[:, None]))
+    out["mismatching_words"] = out["image_words"] + out["id_words"] + out["idbuf_size"] + out["buffer_words"] + out["position_words"]
+    return out
+
+
+def oracle_full_raycast(lib, octree_cpu, root_cpu, rx, ry, pose, depth=11):
+    """One full raycast (raycast_fine_2 over the whole screen) + colorize on the CPU: (screen words, colorized image)."""
+    from oracle import frame as ofr
+    n = rx * ry
+    screen = np.full(4 * n + 64, HOLE, dtype=np.uint32)
+    back = np.zeros(16 * n + 64, dtype=np.float32)
+    tex = np.zeros(n, dtype=np.uint32)
+    cam = ofr.camera_args(*pose, depth)
+    t = lib.max_threads()
+    lib.raycast_fine_2(screen, back, octree_cpu, root_cpu, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], threads=t, gx=rx, gy=ry)
+    lib.raycast_colorize(screen, tex, rx, ry, threads=t)
+    return screen[:n], back[:4 * n], tex
 
 
 def octree_words_per_ray(octree, root, frames=(0, 40)):
@@ -230,23 +361,37 @@ def octree_words_per_ray(octree, root, frames=(0, 40)):
     return l.value / max(1, r.value), i.value / max(1, r.value)
 
 
-def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, frames=48):
+def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, frames=48, cpu=None):
     """BASELINE.json config 3: 3840x2160 on screen bands (stripes dealt round-robin to the ranks, octree replicated): full
     raycasts (every ray stores its colorized pixel into rank 0's frame over NVLink; end-of-frame flag barrier off the
     critical path) and the warped pipeline (reprojection by peer atomics).  Strong scaling: one image, all ranks.  The
     stripe height is a layout parameter chosen per workload: fine stripes balance the full raycast (2160 rows do not
-    divide evenly into 64-row stripes over 8 ranks), coarse ones keep the warped pipeline's halo and id lists short."""
+    divide evenly into 64-row stripes over 8 ranks), coarse ones keep the warped pipeline's halo and id lists short.
+    cpu = (lib, octree, root) of the CPU reference on rank 0: the rank-assembled output is compared with it bit for bit
+    (one full-raycast image; image, id lists and every rank's own rows of the warped pipeline after frame 5)."""
+    import zlib
     RX, RY = 3840, 2160
-    ocl, rc = svo.ocl, svo.raycast
+    n = RX * RY
+    ocl, rc, B = svo.ocl, svo.raycast, svo.bands
 
     def params(f):
         rc.set_camera(*flythrough_pose(f))
         return rc.prepare_params(RX, RY, f)
 
     P = [params(f) for f in range(4 + frames)]
+    PARITY_FRAMES = 6
+    parity = {}
+
+    def gather(obj):
+        if dist is None:
+            return [obj]
+        out = [None] * world if rank == 0 else None
+        dist.gather_object(obj, out, dst=0)
+        return out
 
     def run(stripe_rows, what):
-        db = svo.bands.DistributedBand(octree, root, RX, RY, local_rank, stripe_rows=stripe_rows, dist=dist)
+        db = B.DistributedBand(octree, root, RX, RY, local_rank, stripe_rows=stripe_rows, dist=dist)
+        sr_eff = db.band.lay["SR"]
 
         def fence():
             db.band.sync()
@@ -268,6 +413,13 @@ def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, fr
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t[0])
 
+        def my_rows_crc():
+            """crc32 of the rows this rank owns in buffer 0 (colour words, positions): (rank, crc_colour, crc_xyz)"""
+            rows = B.owned_rows(rank, world, RY, stripe_rows)
+            scr = db.band.read(B.SCREEN, np.uint32, n).reshape(RY, RX)[rows]
+            bck = db.band.read(B.BACK, np.float32, 4 * n).reshape(RY, RX * 4)[rows]
+            return rank, zlib.crc32(np.ascontiguousarray(scr).tobytes()), zlib.crc32(np.ascontiguousarray(bck).tobytes())
+
         if what == "raycast":
             # SVO_FRAME_PINGPONG: consecutive full raycasts alternate between buffers 0 / 2 and between two streams, so one
             # frame's tail (a few long rays) overlaps the next frame's bulk
@@ -279,21 +431,56 @@ def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, fr
                 R.append(q)
             for p in R[:4]:
                 db.band.raycast(p)
+            fence()
+            if cpu is not None or world > 1:             # parity: the writer's assembled image of frame 3 against the CPU reference
+                img = db.band.read(B.TEX, np.uint32, n) if rank == 0 else None
+                if rank == 0 and cpu is not None:
+                    _, _, tex = oracle_full_raycast(cpu[0], cpu[1], cpu[2], RX, RY, flythrough_pose(3))
+                    parity["bands_raycast_3840x2160"] = {"frames": 1, "ranks": world, "image_words": _mism(img, tex), "mismatching_words": _mism(img, tex)}
+                fence()
             ms = timed(db.band.raycast, R[4:4 + frames])
         else:
+            if cpu is not None or world > 1:
+                # parity: frames 0..5 observed at the end -- the writer's image, every rank's id list, every rank's own rows
+                for p in P[:PARITY_FRAMES]:
+                    db.band.frame(p)
+                fence()
+                counts, offsets, ids = db.band.idbuf()
+                mine = gather((rank, counts, ids, my_rows_crc()))
+                img = db.band.read(B.TEX, np.uint32, n) if rank == 0 else None
+                if rank == 0 and cpu is not None:
+                    from oracle import frame as ofr
+                    O = ofr.OracleFrame(cpu[0], cpu[1], cpu[2], RX, RY, threads=cpu[0].max_threads())
+                    for f in range(PARITY_FRAMES):
+                        O.draw(*flythrough_pose(f))
+                    nb = O.nblocks
+                    exp_off = O.idbuf[nb:2 * nb].astype(np.int64)
+                    exp_cnt = np.diff(np.append(exp_off, O.idbuf_size))
+                    id_bad, row_bad = 0, 0
+                    for r, cnt, rid, crc in mine:
+                        blocks = B.owned_blocks(r, world, RX, RY, stripe_rows)
+                        exp_ids = np.concatenate([O.idbuf[2 * nb + exp_off[g]:2 * nb + exp_off[g] + exp_cnt[g]] for g in blocks]) if len(blocks) else np.zeros(0, np.uint32)
+                        id_bad += _mism(cnt, exp_cnt[blocks].astype(np.uint32)) + _mism(rid, exp_ids)
+                        rows = B.owned_rows(r, world, RY, stripe_rows)
+                        e_s = zlib.crc32(np.ascontiguousarray(O.screen[:n].reshape(RY, RX)[rows]).tobytes())
+                        e_b = zlib.crc32(np.ascontiguousarray(O.back[:4 * n].reshape(RY, RX * 4)[rows]).tobytes())
+                        row_bad += int(crc[1] != e_s) + int(crc[2] != e_b)
+                    iw = _mism(img, O.tex)
+                    parity["bands_warped_3840x2160"] = {"frames": PARITY_FRAMES, "ranks": world, "image_words": iw, "id_words": id_bad, "hole_pixels_last_frame": int(O.idbuf_size),
+                                                        "rank_row_sets_differing": row_bad, "mismatching_words": iw + id_bad + row_bad}
+                fence()
             for p in P[:4]:                               # frames 0 and 1 are full raycasts through the hole path
                 db.band.frame(p)
             ms = timed(db.band.frame, P[4:4 + frames])
-        sr = db.band.lay["SR"]
         db.close()
-        return ms, sr
+        return ms, sr_eff
 
     ray_ms, ray_sr = run(args.ray_stripe_rows, "raycast")
     warp_ms, warp_sr = run(args.stripe_rows, "frame")
     return {"ranks": world, "stripe_rows": warp_sr, "ray_stripe_rows": ray_sr, "scaling": "strong", "frames": frames,
             "full_raycast_mrays_per_s": frames * RX * RY / (ray_ms * 1e-3) / 1e6, "full_raycast_ms": ray_ms / frames,
             "warped_fps": frames / (warp_ms * 1e-3), "warped_ms": warp_ms / frames,
-            "exchange": "peer atomicMin / peer gather / halo rows / colorized pixels over NVLink, flag barriers in peer memory; no NCCL"}
+            "exchange": "peer atomicMin / peer gather / halo rows / colorized pixels over NVLink, flag barriers in peer memory; no NCCL"}, parity
 
 
 def builder_bench(svo, path, local_rank):
@@ -328,7 +515,7 @@ def builder_bench(svo, path, local_rank):
                         "column walk on the host, slab decode + the same builder on the GPU (compare with host_rle4_load_s + host_builder_s)"}
 
 
-def terrain14_bench(svo, args, frames=64):
+def terrain14_bench(svo, args, frames=64, with_parity=True):
     """BASELINE.json config 4: fBm fractal terrain at OCTREE_DEPTH 14 (4096^2 columns of a 16384^3 world, 3-voxel shell),
     the flythrough at 8x translation and 4x rotation speed (high hole fraction), 1920x1024, fused frame."""
     rc, ocl = svo.raycast, svo.ocl
@@ -365,11 +552,34 @@ def terrain14_bench(svo, args, frames=64):
             holes.append(rc.idbuf_size() / n)
     rc.set_camera(*pose(8))
     ray_ms = rc.full_raycast_ms(RES_X, RES_Y)
+    parity = None
+    if with_parity:
+        # frames 0..5 of this path against the CPU oracle at depth 14 (the C restatement: oracle/_ref is the reference's
+        # compile-time OCTREE_DEPTH 11): colorized image, id list and idbuf_size of every frame
+        from oracle import binding, frame as ofr
+        orc = binding.get("orc")
+        orc.lib.orc_set_depth(14)
+        try:
+            O = ofr.OracleFrame(orc, octree, root, RES_X, RES_Y, threads=orc.max_threads(), depth=14)
+            nb = O.nblocks
+            rc.reset_frames()
+            bad = {"image_words": 0, "id_words": 0, "idbuf_size": 0}
+            for f in range(6):
+                O.draw(*pose(f))
+                rc.draw_prepared(P[f], sync=True)
+                bad["image_words"] += _mism(rc.read_frame(RES_X, RES_Y), O.tex)
+                gsz = rc.idbuf_size()
+                bad["idbuf_size"] += int(gsz != O.idbuf_size)
+                idb = rc.S.mem_idbuffer.to_numpy(np.uint32, 2 * nb + max(gsz, O.idbuf_size))
+                bad["id_words"] += _mism(idb[nb:2 * nb + O.idbuf_size], O.idbuf[nb:2 * nb + O.idbuf_size])
+        finally:
+            orc.lib.orc_set_depth(11)
+        parity = dict(frames=6, oracle="C restatement (depth 14)", hole_pixels_last_frame=int(O.idbuf_size), **bad, mismatching_words=sum(bad.values()))
     rc.raycast_exit()
     return {"warped_fps": frames / (ms * 1e-3), "ms_per_frame": ms / frames, "hole_fraction_mean": float(np.mean(holes)),
             "full_raycast_mrays_per_s": n / (ray_ms * 1e-3) / 1e6, "octree_mb": round(octree.nbytes / 2 ** 20, 1),
             "voxels": stats["num_voxels"], "depth": 14, "host_build_s": round(build_s, 1),
-            "config": "fBm terrain 4096x4096 columns at depth 14, camera 8x translation / 4x rotation of the config-2 path"}
+            "config": "fBm terrain 4096x4096 columns at depth 14, camera 8x translation / 4x rotation of the config-2 path"}, parity
 
 
 def main():
@@ -379,6 +589,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the GPU output with the CPU reference (development aid)")
+    ap.add_argument("--parity-frames", type=int, default=12, help="frames 0.. of the flythrough compared with the serial reference")
     ap.add_argument("--profile-frames", type=int, default=32)
     ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
     ap.add_argument("--ray-stripe-rows", type=int, default=16, help="stripe height of the banded full raycast at 3840x2160")
@@ -398,23 +610,28 @@ def main():
     path, scene_name = scene_path()
 
     if args.impl == "reference":
+        # The reference's own CPU path, stock: its loader and octree builder (RLE4::load -> convert_tree_blocks) and its
+        # kernel.cl through oracle/_ref; none of this repo's kernels, builder or library (the scene file comes from the
+        # plain host program svo_make_scene when data/Imrodh.rle4 is absent).
         if rank != 0:
             return 0
-        svo = load_package()           # host-side scene code only (no GPU call): builds the same octree
-        make_scene(svo, path)
-        octree, root, _ = svo.scene.octree_init(path)
-        r = cpu_arm(octree, root, args.steps, args.warmup, budget_s=150.0)
+        make_scene(path)
+        lib, kind, octree, root = oracle_octree(path)
+        r = cpu_arm(lib, kind, octree, root, args.steps, args.warmup, budget_s=150.0)
         line = {"impl": "reference", "metric": "warped_pipeline_fps_1920x1024", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": r["frames_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-                "config": {"workload": workload_name(scene_name)},
+                "config": bench_config(scene_name, args.steps, args.warmup),
                 "full_raycast_mrays_per_s": r["full_raycast_mrays_per_s"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "opencl_cpu_runtime")},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        fm = cpu_arm_fast_math(octree, root, args.warmup)
+        if fm:
+            line["cpu_baseline_fast_math"] = fm
         print(json.dumps(line))
         return 0
 
-    host_cpus = pin_to_gpu_numa(local_rank)
+    host_cpus = pin_to_gpu_numa(local_rank, world)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -423,16 +640,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     svo = load_package()
     if rank == 0:
-        make_scene(svo, path)
+        make_scene(path)
     if world > 1:
         dist.barrier()
     octree, root, stats = svo.scene.octree_init(path)          # .rle4 loader -> direct compact-octree builder
     rc, ocl = svo.raycast, svo.ocl
     if args.bands_only:
         rc.S.mode = args.mode                                     # prepare_params() without raycast_init()
-        out = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args)
+        cpu = None
+        if rank == 0 and not args.no_parity:
+            lib, _, o_cpu, r_cpu = oracle_octree(path)
+            cpu = (lib, o_cpu, r_cpu)
+        out, bpar = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args, cpu=cpu)
         if rank == 0:
-            print(json.dumps({"bands_3840x2160": out}))
+            print(json.dumps({"bands_3840x2160": out, "parity": bpar}))
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -572,8 +793,22 @@ def main():
     fps = world * args.steps / (ms_max * 1e-3)
     e2e_fps = world * args.steps / (e2e_ms_max * 1e-3)
 
+    # ---- parity of the measured configuration: the same frames, observed, against the serial reference (rank 0) ----
+    parity, cpu = {}, None
+    if rank == 0 and not args.no_parity:
+        lib, cpu_kind, o_cpu, r_cpu = oracle_octree(path)
+        cpu = (lib, o_cpu, r_cpu)
+        parity["oracle"] = ("reference kernel.cl + octree.h + Rle4.cpp via oracle/_ref, serial work-item order" if cpu_kind == "reference"
+                            else "C restatement oracle/svo_oracle.c (oracle/_ref not built on this box)")
+        parity["octree"] = {"words": int(len(o_cpu)), "mismatching_words": _mism(octree, o_cpu) + int(root != r_cpu),
+                            "what": "compact octree of the product's loader + builder vs the reference's RLE4::load -> convert_tree_blocks"}
+        parity["flythrough_1920x1024"] = parity_flythrough(svo, lib, o_cpu, r_cpu, P, min(args.parity_frames, total), args.mode)
+
     if rank == 0:
         peak, peak_src = measured_peak()
+        clocks = sampler.summary()
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         # algorithmic bytes per launch; traversal: (4L+16) per ray (+4 index word for hole rays)
         L, iters = octree_words_per_ray(octree, root)
         per_frame_ms = {k: v[0] / pf for k, v in prof.items()}
@@ -594,29 +829,45 @@ def main():
                "k_rays_tile": (4.0 * L + 16.0) * tile_rays, "k_rays_holes": (4.0 * L + 20.0) * H,
                "k_copy_colorize": 40.0 * n,                                       # only when the host observes the buffers
                "k_fill_list": 28.0 * resid_px, "k_apply_patches": 12.0 * resid_px}
+        rays_of = {"k_rays_holes": H, "k_raycast_holes": H, "k_rays_tile": tile_rays, "k_raycast_fine_2": tile_rays}
         d_ms, d_cnt = prof[dom]
         avg_ms = d_ms / max(1, d_cnt)
-        achieved = alg.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
+        if dom in rays_of:
+            # a traversal kernel dominates the frame: HBM is not its roof (0.2 MB of DRAM traffic per launch); the algorithmic
+            # bytes and the HBM fraction are kept next to the issue roof for completeness
+            roof = issue_roofline(dom, rays_of[dom], avg_ms, sms, sm_mhz)
+            hbm_ach = alg.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
+            roof.update(algorithmic_bytes_per_launch=alg.get(dom), hbm_achieved_gbs=hbm_ach, hbm_frac=hbm_ach / peak, hbm_peak_gbs=peak,
+                        octree_words_per_ray=L, iterations_per_ray=iters,
+                        note="latency bound: the launch lasts as long as its slowest warp (profiles/r2_ray_latency.md); achieved Mrays/s of such a sparse launch is far below any throughput roof by construction")
+        else:
+            achieved = alg.get(dom, 0.0) / (avg_ms * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg.get(dom), "avg_launch_ms": avg_ms}
+        roof["peak_source"] = peak_src
+        config = bench_config(scene_name, args.steps, args.warmup)
         line = {"metric": "warped_pipeline_fps_1920x1024", "value": fps, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-                "config": {"workload": workload_name(scene_name),
-                           "octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
-                           "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} ({'a different camera path' if args.distinct_paths else 'the config-2 flythrough'} on every GPU, octree replicated, no communication)",
-                           "l2_note": "working set per frame (2 x 20 B/pixel x 1.97 Mpixel + octree) exceeds nothing by construction: inputs change every frame; "
-                                      "no L2 flush between frames (a frame reads what the previous frame wrote, as in the real pipeline)",
-                           "hole_fraction_last_frame": hole_frac},
+                "config": config,
+                "details": {"octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
+                            "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} ({'a different camera path' if args.distinct_paths else 'the config-2 flythrough'} on every GPU, octree replicated, no communication)",
+                            "hole_fraction_last_frame": hole_frac},
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus,
                         "passes_fps": [round(world * args.steps / (v * 1e-3), 1) for v in e2e_passes_ms], "value_is": "median of the passes",
                         "d2h_link_gbs": d2h_gbs, "d2h_used_gbs": e2e_fps / world * n * 3 / 1e9},
-                "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": sampler.summary(),
+                "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": clocks,
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
-                "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": ncu_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg.get(dom),
-                             "avg_launch_ms": avg_ms, "octree_words_per_ray": L, "iterations_per_ray": iters}}
-        # the same figure for the frame's dominant bandwidth kernel (the traversal kernels are latency bound)
+                "roofline": roof}
+        # the whole frame against the HBM roof: SURVEY 8(d)'s bytes (the warp passes at 80-100 B/pixel + the rays' node words)
+        frame_bytes = (4 + 4 + 16.0 * V / n + 20.0 * W / n + 4 + 4.0 * H / n + 40 + 4 + 8) * n + (4.0 * L + 16.0) * (H + tile_rays)
+        fb_ach = frame_bytes / (ms_max / args.steps * 1e-3) / 1e9
+        line["roofline_frame"] = {"kernel": "whole frame (all launches)", "bound": "hbm", "achieved": fb_ach, "peak": peak, "unit": "GB/s", "frac": fb_ach / peak,
+                                  "algorithmic_bytes_per_frame": frame_bytes, "ms_per_frame": ms_max / args.steps,
+                                  "note": "SURVEY 8(d): clear 4N + reprojection 4N+16V+20W + hole gather 4N+4H + cache copy 40N + gap filter 4N + colorize 8N + (4L+16) per ray; the frame is a chain of latencies, not bandwidth bound"}
+        # the frame's dominant bandwidth kernel
         stream_k = [k for k in ("k_copy_colorize", "k_resolve_gather", "k_proj_scatter2", "k_memcpy", "k_proj_resolve") if k in prof]
         if stream_k:
             sk = max(stream_k, key=lambda k: per_frame_ms[k])
@@ -624,27 +875,39 @@ def main():
             s_ach = alg[sk] / (s_ms * 1e-3) / 1e9
             line["roofline_streaming"] = {"kernel": sk, "bound": "hbm", "achieved": s_ach, "peak": peak, "unit": "GB/s", "frac": s_ach / peak,
                                           "traffic": ncu_traffic(sk), "algorithmic_bytes_per_launch": alg[sk], "avg_launch_ms": s_ms}
-        # and for the other half of the metric, the full-screen traversal kernel (issue bound: DESIGN.md section 4)
+        # and the other half of the metric, the full-screen traversal kernel: issue bound
+        fr = issue_roofline("k_raycast_fine_2", n, float(np.median(ray_ms)), sms, sm_mhz)
         fr_bytes = (4.0 * L + 16.0) * n
-        fr_ach = fr_bytes / (float(np.median(ray_ms)) * 1e-3) / 1e9
-        line["roofline_full_raycast"] = {"kernel": "k_raycast_fine_2", "bound": "hbm", "achieved": fr_ach, "peak": peak, "unit": "GB/s", "frac": fr_ach / peak,
-                                         "traffic": ncu_traffic("k_raycast_fine_2"), "algorithmic_bytes_per_launch": fr_bytes,
-                                         "avg_launch_ms": float(np.median(ray_ms)), "note": "instruction-issue bound (ncu: issue slots 83 % busy, 21 of 32 lanes active); HBM is 1 % busy"}
+        fr.update(algorithmic_bytes_per_launch=fr_bytes, hbm_achieved_gbs=fr_bytes / (float(np.median(ray_ms)) * 1e-3) / 1e9, hbm_peak_gbs=peak)
+        line["roofline_full_raycast"] = fr
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_arm(octree, root, steps=24, warmup=args.warmup, budget_s=25.0)
+            if cpu is None:
+                lib, cpu_kind, o_cpu, r_cpu = oracle_octree(path)
+            r = cpu_arm(lib, cpu_kind, o_cpu, r_cpu, steps=24, warmup=args.warmup, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "opencl_cpu_runtime")}
             line["cpu_baseline"]["full_raycast_mrays_per_s"] = r["full_raycast_mrays_per_s"]
+            fm = cpu_arm_fast_math(o_cpu, r_cpu, args.warmup)
+            if fm:
+                line["cpu_baseline_fast_math"] = fm
     rc.raycast_exit()
     extras = {}
     if not args.no_extras:
         extras["view_parallel_64_cameras"] = {"grays_per_s": 64 * n / (cams_ms_max * 1e-3) / 1e9, "ms": cams_ms_max,
                                               "config": "64 poses of the flythrough (every 4th frame), full raycast 1920x1024 each, dealt round-robin to the ranks, no communication; per rank one svo_raycast_batch (buffers 0 / 2 and two streams alternate, consecutive cameras overlap)"}
-        extras["bands_3840x2160"] = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args)
+        extras["bands_3840x2160"], bpar = band_bench(svo, octree, root, rank, world, local_rank, dist if world > 1 else None, torch, args, cpu=cpu)
+        parity.update(bpar)
         if world == 1:
-            extras["terrain_depth14"] = terrain14_bench(svo, args)
+            extras["terrain_depth14"], tpar = terrain14_bench(svo, args, with_parity=not args.no_parity)
+            if tpar:
+                parity["terrain_depth14"] = tpar
             extras["octree_build"] = builder_bench(svo, path, local_rank)
     if rank == 0:
         line.update(extras)
+        if parity:
+            checks = [v for v in parity.values() if isinstance(v, dict) and "mismatching_words" in v]
+            parity["frames_checked"] = int(sum(v.get("frames", 0) for v in checks))
+            parity["mismatching_words"] = int(sum(v["mismatching_words"] for v in checks))
+            line["parity"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

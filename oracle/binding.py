@@ -19,6 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libsvo_ref.so")
+REF_FAST_SO = os.path.join(HERE, "_ref", "libsvo_ref_fast.so")     # -O3 -ffast-math twin (src/ocl.h:47 -cl-fast-relaxed-math): timing only
 ORC_SO = os.path.join(HERE, "libsvo_oracle.so")
 
 u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
@@ -35,6 +36,34 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def have_ref_fast():
+    return os.path.exists(REF_FAST_SO)
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def quiet_stdout():
+    """The reference's loader prints its progress with printf (src/octree/Rle4.cpp:22-89): keep it off this process' stdout
+    (bench.py prints one JSON line there)."""
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        yield
+    finally:
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
 def _vec4(v):
     a = np.zeros(4, dtype=np.float32)
     v = np.asarray(v, dtype=np.float32).ravel()
@@ -46,8 +75,10 @@ class CpuOracle:
     """One loaded oracle library (prefix 'ref' or 'orc')."""
 
     def __init__(self, prefix):
+        fast = prefix == "ref_fast"
+        prefix = "ref" if fast else prefix
         self.prefix = prefix
-        path = REF_SO if prefix == "ref" else ORC_SO
+        path = REF_FAST_SO if fast else REF_SO if prefix == "ref" else ORC_SO
         if prefix == "orc" and (not os.path.exists(path)
                                 or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "svo_oracle.c"))):
             build("oracle")
@@ -87,6 +118,11 @@ class CpuOracle:
         self._fillhole2 = fn("raycast_fillhole2", None, i, i, i, i, u32p, vp, i, i, i)
         self._colorize = fn("raycast_colorize", None, i, i, i, i, i, u32p, u32p, i, i)
         self._max_threads = fn("max_threads", i)
+        # multi-threaded forms for the timed CPU baseline (bench.py); raycast_proj_mt is the racy kernel run work-group-parallel
+        self._memset_mt = fn("memset_mt", None, i, u32p, u, u, i)
+        self._memcpy_mt = fn("memcpy_mt", None, i, u32p, u, u32p, u, i)
+        self._proj_mt = fn("raycast_proj_mt", None, i, i, i, i, i, u32p, f32p, vp, vp, vp, i, i, i, i, f32p, f32p, f32p, f32p)
+        self._fillhole2_mt = fn("raycast_fillhole2_mt", None, i, i, i, i, i, u32p, vp, i, i, i)
 
     # ---- octree build -------------------------------------------------------
     def build_octree(self, x, y, z, rgba):
@@ -97,9 +133,11 @@ class CpuOracle:
         return self._finish()
 
     def build_octree_rle4(self, path, palette=0):
-        self._reset()
-        self._load_rle4(os.fsencode(path), palette, 0, 0, 0)
-        return self._finish()
+        """RLE4::load -> set_voxel -> convert_tree_blocks (src/raycast.h:13-46)."""
+        with quiet_stdout():
+            self._reset()
+            self._load_rle4(os.fsencode(path), palette, 0, 0, 0)
+            return self._finish()
 
     def _finish(self):
         root = self._convert()
@@ -117,15 +155,27 @@ class CpuOracle:
         return int(self._max_threads())
 
     # ---- kernels; buffers are numpy arrays modified in place -------------------
-    def memset(self, dst, dstofs_words, val, nwords):
-        self._memset(nwords, dst, dstofs_words, val)
+    def memset(self, dst, dstofs_words, val, nwords, threads=1):
+        if threads > 1:
+            self._memset_mt(nwords, dst, dstofs_words, val, threads)
+        else:
+            self._memset(nwords, dst, dstofs_words, val)
 
-    def memcpy(self, dst, dstofs_words, src, srcofs_words, nwords):
-        self._memcpy(nwords, dst, dstofs_words, src, srcofs_words)
+    def memcpy(self, dst, dstofs_words, src, srcofs_words, nwords, threads=1):
+        if threads > 1:
+            self._memcpy_mt(nwords, dst, dstofs_words, src, srcofs_words, threads)
+        else:
+            self._memcpy(nwords, dst, dstofs_words, src, srcofs_words)
 
-    def raycast_proj(self, screen, back, res_x, res_y, frame, ofs_add, m0, mx, my, mz):
-        self._proj(res_x, res_y, 16, 16, screen, back, None, None, None, res_x, res_y, frame, ofs_add,
-                   _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz))
+    def raycast_proj(self, screen, back, res_x, res_y, frame, ofs_add, m0, mx, my, mz, racy_threads=1):
+        """racy_threads > 1: the kernel work-group-parallel with its payload race, as an OpenCL CPU runtime runs it -- for
+        timing only; the serial form (default) is the defined outcome the parity checks use."""
+        if racy_threads > 1:
+            self._proj_mt(res_x, res_y, 16, 16, racy_threads, screen, back, None, None, None, res_x, res_y, frame, ofs_add,
+                          _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz))
+        else:
+            self._proj(res_x, res_y, 16, 16, screen, back, None, None, None, res_x, res_y, frame, ofs_add,
+                       _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz))
 
     def raycast_counthole(self, screen, idbuf, res_x, res_y, frame=0, threads=1):
         self._counthole(res_x // 16, res_y // 16, 16, 16, threads, screen, None, idbuf, res_x, res_y, frame)
@@ -163,8 +213,11 @@ class CpuOracle:
         """kernel.cl:342-401 with the launch geometry of its (disabled) call site, src/raycast.h:209."""
         self._fillhole(res_x, res_y, 16, 16, threads, screen, back, xbuf, ybuf, None, res_x, res_y, frame)
 
-    def raycast_fillhole2(self, screen, res_x, res_y, frame=0):
-        self._fillhole2(res_x, res_y, 16, 16, screen, None, res_x, res_y, frame)
+    def raycast_fillhole2(self, screen, res_x, res_y, frame=0, threads=1):
+        if threads > 1:
+            self._fillhole2_mt(res_x, res_y, 16, 16, threads, screen, None, res_x, res_y, frame)
+        else:
+            self._fillhole2(res_x, res_y, 16, 16, screen, None, res_x, res_y, frame)
 
     def raycast_colorize(self, screen, tex, w, h, threads=1):
         self._colorize(w, h, 16, 16, threads, screen, tex, w, h)

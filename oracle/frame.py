@@ -63,10 +63,14 @@ def camera_args(pos, rot, depth=11):
 class OracleFrame:
     """State of the reference's frame loop (4 colour + 4 coordinate buffers, id buffer, frame counter)."""
 
-    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11, cache_rotation=False):
+    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11, cache_rotation=False, timed=False):
         """cache_rotation: the copy target the reference has in a comment, `((frame>>4)%2)+1` (src/raycast.h:395), instead of
         the hard-wired 2 -- the variant that makes the triple buffer real."""
         self.cache_rotation = cache_rotation
+        # timed=True (bench.py's CPU baseline): every kernel work-group-parallel on `threads` host threads, the way an OpenCL
+        # CPU runtime would run the frame -- raycast_proj with its payload race.  The result is then not the defined
+        # (serial) outcome; parity checks use timed=False.
+        self.timed = timed
         self.o, self.octree, self.root = orc, octree, root
         self.res_x, self.res_y, self.threads, self.depth = res_x, res_y, threads, depth
         n = res_x * res_y
@@ -90,11 +94,12 @@ class OracleFrame:
         frame = self.frame
         cam = camera_args(pos, rot, self.depth)
         v0 = cam["v0"]
+        mt = t if self.timed else 1
         if frame < 2:                                                   # :150-154
-            o.memset(self.screen, 0, HOLE, n * 4)
-        o.memset(self.screen, 0, HOLE, n)                               # :157
+            o.memset(self.screen, 0, HOLE, n * 4, threads=mt)
+        o.memset(self.screen, 0, HOLE, n, threads=mt)                   # :157
         for i in range(2):                                              # :177-198
-            o.raycast_proj(self.screen, self.back, rx, ry, frame, (i + 1) * n, v0, *cam["rows"])
+            o.raycast_proj(self.screen, self.back, rx, ry, frame, (i + 1) * n, v0, *cam["rows"], racy_threads=mt)
         if stop_after == "proj":
             return cam
         o.raycast_counthole(self.screen, self.idbuf, rx, ry, frame, t)  # :272-282
@@ -112,18 +117,21 @@ class OracleFrame:
         if stop_after == "rays":
             return cam
         target = ((frame >> 4) % 2) + 1 if self.cache_rotation else 2   # :395
-        o.memcpy(self.screen, target * n, self.screen, 0, n)            # :394-405
+        o.memcpy(self.screen, target * n, self.screen, 0, n, threads=mt)    # :394-405
         back_u = self.back.view(np.uint32)
-        o.memcpy(back_u, target * n * 4, back_u, 0, n * 4)
+        o.memcpy(back_u, target * n * 4, back_u, 0, n * 4, threads=mt)
         if stop_after == "copy":
             return cam
-        o.raycast_fillhole2(self.screen, rx, ry, frame)                 # :411-422
+        o.raycast_fillhole2(self.screen, rx, ry, frame, threads=t)      # :411-422 (snapshot semantics: race free)
         o.raycast_colorize(self.screen, self.tex, rx, ry, t)            # :429-437
         return cam
 
 
 def flythrough_pose(f):
-    """Scripted camera of SURVEY.md 8(d) config 2 (a definition of this repo, not of the reference)."""
+    """Scripted camera of SURVEY.md 8(d) config 2 (a definition of this repo, not of the reference).  rot.x is +0.6, not the
+    survey's -0.6: with the reference's matrix conventions (ext/mathlib/_matrix44.h:529-541) a negative pitch points the camera
+    at the sky -- 98.5 % of the primary rays leave the world at once -- while +0.6 looks down at the scene the way the
+    reference's screenshot does.  bench.py uses the same path."""
     pos = (1.0 + f * 0.2357, 50.0, 1.0 + f * 0.2357)
-    rot = (-0.6 + 0.1 * math.sin(2.0 * math.pi * f / 128.0), 0.8 + 0.005 * f, 0.0)
+    rot = (0.6 + 0.1 * math.sin(2.0 * math.pi * f / 128.0), 0.8 + 0.005 * f, 0.0)
     return pos, rot

@@ -64,9 +64,11 @@ static inline int get_local_id(int d)   { return cl_item.lid[d]; }
 static inline int get_local_size(int d) { return cl_item.lsz[d]; }
 
 // cl_khr_global_int32_extended_atomics: unsigned min, returns the old value
+// (a real atomic: the timed CPU baseline runs raycast_proj work-group-parallel, as an OpenCL CPU runtime would; serially it
+// is the same read-compare-write)
 static inline unsigned int atom_min(unsigned int *p, unsigned int v)
 {
-    unsigned int old = *p;
-    if (v < old) *p = v;
+    unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return old;
 }

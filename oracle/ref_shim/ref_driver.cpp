@@ -235,6 +235,57 @@ void ref_raycast_fine(int gx, int gy, int lx, int ly, uint *screen, float *back,
     });
 }
 
+// ---------------- multi-threaded forms for the TIMED CPU baseline (bench.py) ----------------------------------------
+// An OpenCL CPU runtime runs every kernel work-group-parallel; so does the baseline.  memset / memcpy / fillhole2 (snapshot
+// mode: every thread works on a private copy of the pre-pass image) give the serial result.  raycast_proj_mt runs the
+// reference kernel as it stands, atomics and payload race included (src/raycast.h:182-197): its output can differ from the
+// serial outcome in the pixels where two sources tie, which is why parity checks use the serial entry points above and
+// this one only feeds the clock.
+void ref_memset_mt(int gx, uint *dst, uint dstofs, uint val, int threads)
+{
+    ndrange(gx, 1, 256, 1, threads, [&] { cl_memset(dst, dstofs, val); });
+}
+void ref_memcpy_mt(int gx, uint *dst, uint dstofs, uint *src, uint srcofs, int threads)
+{
+    ndrange(gx, 1, 256, 1, threads, [&] { cl_memcpy(dst, dstofs, src, srcofs); });
+}
+void ref_raycast_proj_mt(int gx, int gy, int lx, int ly, int threads, uint *screen, float *back,
+                         int *xb, int *yb, int *zb, int res_x, int res_y, int frame, int ofs_add,
+                         const float *m0, const float *mx, const float *my, const float *mz)
+{
+    ndrange(gx, gy, lx, ly, threads, [&] {
+        raycast_proj(screen, back, xb, yb, zb, res_x, res_y, frame, ofs_add, f4(m0), f4(mx), f4(my), f4(mz));
+    });
+}
+void ref_raycast_fillhole2_mt(int gx, int gy, int lx, int ly, int threads, uint *screen, float *back, int res_x, int res_y, int frame)
+{
+    if (threads <= 1) { ref_raycast_fillhole2(gx, gy, lx, ly, screen, back, res_x, res_y, frame); return; }
+    const size_t n = (size_t)res_x * res_y, nsnap = n + 3 * (size_t)res_x + 8;     // the 5x5 search reads up to 2 rows + 2 words past the image
+    std::vector<uint> out(screen, screen + n);
+    gx = round_up(lx, gx); gy = round_up(ly, gy);
+    const int ngx = gx / lx, ngy = gy / ly;
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<uint> mine(screen, screen + nsnap);                               // private pre-pass image
+#pragma omp for schedule(dynamic, 4)
+        for (int g = 0; g < ngx * ngy; ++g) {
+            const int bx = (g % ngx) * lx, by = (g / ngx) * ly;
+            for (int y = 0; y < ly; ++y)
+                for (int x = 0; x < lx; ++x) {
+                    cl_item = ClItem{{bx + x, by + y}, {x, y}, {lx, ly}};
+                    const int idx = bx + x, idy = by + y;
+                    if (idx >= res_x || idy >= res_y) { raycast_fillhole2(mine.data(), back, res_x, res_y, frame); continue; }
+                    const size_t ofs = (size_t)idy * res_x + idx;
+                    const uint before = mine[ofs];
+                    raycast_fillhole2(mine.data(), back, res_x, res_y, frame);
+                    out[ofs] = mine[ofs];
+                    mine[ofs] = before;
+                }
+        }
+    }
+    std::copy(out.begin(), out.end(), screen);
+}
+
 int ref_max_threads() { return omp_get_max_threads(); }
 
 } // extern "C"

@@ -488,14 +488,27 @@ void orc_memcpy(int gx, uint32_t *dst, uint32_t dstofs, uint32_t *src, uint32_t 
     for (int i = 0; i < n; ++i) dst[dstofs + (uint32_t)i] = src[srcofs + (uint32_t)i];
 }
 
+/* multi-threaded forms for the timed CPU baseline (same results: disjoint words) */
+void orc_memset_mt(int gx, uint32_t *dst, uint32_t dstofs, uint32_t val, int threads)
+{
+    const int n = round_up(256, gx);
+#pragma omp parallel for schedule(static) num_threads(threads < 1 ? 1 : threads)
+    for (int i = 0; i < n; ++i) dst[(uint32_t)i + dstofs] = val;
+}
+void orc_memcpy_mt(int gx, uint32_t *dst, uint32_t dstofs, uint32_t *src, uint32_t srcofs, int threads)
+{
+    const int n = round_up(256, gx);
+#pragma omp parallel for schedule(static) num_threads(threads < 1 ? 1 : threads)
+    for (int i = 0; i < n; ++i) dst[dstofs + (uint32_t)i] = src[srcofs + (uint32_t)i];
+}
+
 /* kernel/kernel.cl:472-592, serial outcome.  Mixed float/double expressions are kept exactly as
  * C evaluates the reference text: `+0.0`, `-0.0` and `<0.05` promote to double (:549,:552-553). */
-void orc_raycast_proj(int gx, int gy, int lx, int ly, uint32_t *screen, float *back, int *xb, int *yb, int *zb,
-                      int res_x, int res_y, int frame, int ofs_add,
+static void proj_impl(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back,
+                      int res_x, int res_y, int ofs_add,
                       const float *m0, const float *mx, const float *my, const float *mz)
 {
-    (void)xb; (void)yb; (void)zb; (void)frame;
-    NDRANGE_BEGIN(gx, gy, lx, ly, 1)
+    NDRANGE_BEGIN(gx, gy, lx, ly, threads)
         const int idx = gid0, idy = gid1;
         if (idx >= res_x || idy >= res_y) continue;
         const uint32_t srcofs = (uint32_t)(idy * res_x + idx + ofs_add);
@@ -514,11 +527,30 @@ void orc_raycast_proj(int gx, int gy, int lx, int ly, uint32_t *screen, float *b
         const size_t ofs = (size_t)scry * res_x + scrx;
         const uint32_t sz = (uint32_t)(int)(phz * 1000) << 8;
         const uint32_t val = sz + (col & 255);
-        if ((screen[ofs] & 0xffffff00u) <= sz) continue;                    /* :571 */
-        { const uint32_t old = screen[ofs]; if (val < old) screen[ofs] = val; if (old < val) continue; } /* atom_min :572 */
-        if (screen[ofs] != val) continue;                                   /* :579 */
+        if ((__atomic_load_n(&screen[ofs], __ATOMIC_RELAXED) & 0xffffff00u) <= sz) continue;   /* :571 */
+        {   /* atom_min :572 (a real atomic: the _mt form runs work-group-parallel; serially it is read-compare-write) */
+            uint32_t old = __atomic_load_n(&screen[ofs], __ATOMIC_RELAXED);
+            while (val < old && !__atomic_compare_exchange_n(&screen[ofs], &old, val, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            if (old < val) continue;
+        }
+        if (__atomic_load_n(&screen[ofs], __ATOMIC_RELAXED) != val) continue;                  /* :579 */
         back[ofs * 4 + 0] = pcx; back[ofs * 4 + 1] = pcy; back[ofs * 4 + 2] = pcz; back[ofs * 4 + 3] = phz;
     NDRANGE_END
+}
+void orc_raycast_proj(int gx, int gy, int lx, int ly, uint32_t *screen, float *back, int *xb, int *yb, int *zb,
+                      int res_x, int res_y, int frame, int ofs_add,
+                      const float *m0, const float *mx, const float *my, const float *mz)
+{
+    (void)xb; (void)yb; (void)zb; (void)frame;
+    proj_impl(gx, gy, lx, ly, 1, screen, back, res_x, res_y, ofs_add, m0, mx, my, mz);
+}
+/* the kernel as an OpenCL CPU runtime would run it: work-group-parallel, payload race included -- timing only */
+void orc_raycast_proj_mt(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back, int *xb, int *yb, int *zb,
+                         int res_x, int res_y, int frame, int ofs_add,
+                         const float *m0, const float *mx, const float *my, const float *mz)
+{
+    (void)xb; (void)yb; (void)zb; (void)frame;
+    proj_impl(gx, gy, lx, ly, threads, screen, back, res_x, res_y, ofs_add, m0, mx, my, mz);
 }
 
 /* 2x2 cell of holes?  kernel/kernel.cl:266-271 / :327-332, HOLE_PIXEL_THRESHOLD 4 */
@@ -682,13 +714,19 @@ static uint32_t fillhole2_pixel(const uint32_t *s, int ofs, int res_x)
     return col;
 }
 
+void orc_raycast_fillhole2_mt(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back, int res_x, int res_y, int frame);
 void orc_raycast_fillhole2(int gx, int gy, int lx, int ly, uint32_t *screen, float *back, int res_x, int res_y, int frame)
+{
+    orc_raycast_fillhole2_mt(gx, gy, lx, ly, 1, screen, back, res_x, res_y, frame);
+}
+/* snapshot semantics make the pass race free: work-group-parallel gives the same image */
+void orc_raycast_fillhole2_mt(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back, int res_x, int res_y, int frame)
 {
     (void)back; (void)frame;
     const size_t n = (size_t)res_x * res_y, nsnap = n + 2 * (size_t)res_x + 4;
     uint32_t *snap = (uint32_t *)malloc(nsnap * 4);
     memcpy(snap, screen, nsnap * 4);
-    NDRANGE_BEGIN(gx, gy, lx, ly, 1)
+    NDRANGE_BEGIN(gx, gy, lx, ly, threads)
         const int idx = gid0, idy = gid1;
         if (idx >= res_x - 1 || idy >= res_y - 1 || idx <= 1 || idy <= 1) continue;
         const int ofs = idy * res_x + idx;

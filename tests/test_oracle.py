@@ -170,3 +170,36 @@ def test_disabled_kernel_fine_matches_reference(orc, ref, frame):
     changed = (a_s != screen).reshape(4, ry, rx)[0]
     assert changed.sum() > 0.8 * (rx // 4) * (ry // 4)
     assert not changed[:, :add_x].any() and not changed[:add_y, :].any()
+
+
+# ---- multi-threaded forms used by bench.py's timed CPU baseline ------------------------------------------------------
+@pytest.mark.parametrize("which", ["ref", "orc"])
+def test_threaded_baseline_kernels_match_serial(which, orc, ref):
+    """memset / memcpy / fillhole2 (snapshot mode) run work-group-parallel must leave exactly the serial result; the racy
+    raycast_proj_mt (an OpenCL CPU runtime's schedule) must at least agree wherever the serial outcome has no depth tie."""
+    lib = ref if which == "ref" else orc
+    octree, root = orc.build_octree(*scenes.small_world())
+    rx, ry = 320, 192
+    n = rx * ry
+    A = fr.OracleFrame(lib, octree, root, rx, ry, threads=4)
+    B = fr.OracleFrame(lib, octree, root, rx, ry, threads=4, timed=True)
+    for f in range(6):
+        pos, rot = (10 + 0.4 * f, 22, 9 + 0.3 * f), (0.4, 0.7 + 0.02 * f, 0.0)
+        A.draw(pos, rot)
+        B.draw(pos, rot)
+    # the gap filter and the copies are deterministic: given the same pre-filter frame they produce the same words
+    s = A.screen.copy()
+    lib.raycast_fillhole2(s, rx, ry, 0, threads=1)
+    t = A.screen.copy()
+    lib.raycast_fillhole2(t, rx, ry, 0, threads=4)
+    assert np.array_equal(s, t)
+    d1, d2 = np.zeros(4 * n + 64, np.uint32), np.zeros(4 * n + 64, np.uint32)
+    lib.memcpy(d1, n, A.screen, 0, 2 * n, threads=1)
+    lib.memcpy(d2, n, A.screen, 0, 2 * n, threads=4)
+    assert np.array_equal(d1, d2)
+    lib.memset(d1, 5, 0xABCD, n, threads=1)
+    lib.memset(d2, 5, 0xABCD, n, threads=4)
+    assert np.array_equal(d1, d2)
+    # racy projection: same id counts within a small margin, and the images agree on almost every pixel
+    same = np.count_nonzero(A.tex == B.tex) / n
+    assert same > 0.99, same

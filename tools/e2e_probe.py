@@ -9,7 +9,7 @@ import bench
 from __graft_entry__ import load_package
 svo = load_package()
 path, _ = bench.scene_path()
-bench.make_scene(svo, path)
+bench.make_scene(path)
 octree, root, _ = svo.scene.octree_init(path)
 rc, ocl = svo.raycast, svo.ocl
 RX, RY = 1920, 1024

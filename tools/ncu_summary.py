@@ -49,13 +49,20 @@ def main():
         UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         acc = {}
         ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        ii, il, ia = hdr.index("smsp__inst_executed.sum"), hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio"), hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")
+
+        def num(x):
+            return float(x.replace(",", ""))
         for r in rows[2:]:
             k = r[ki].split("(")[0].replace("void ", "").replace("svo::", "").split("<")[0]
-            b = float(r[ir].replace(",", "")) * UNIT.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * UNIT.get(units[iw], 1.0)
-            acc.setdefault(k, []).append((b, float(r[it].replace(",", ""))))
+            b = num(r[ir]) * UNIT.get(units[ir], 1.0) + num(r[iw]) * UNIT.get(units[iw], 1.0)
+            acc.setdefault(k, []).append((b, num(r[it]), num(r[ii]), num(r[il]), num(r[ia])))
         out = json.load(open(sys.argv[2])) if os.path.exists(sys.argv[2]) else {}
         for k, v in acc.items():
-            out[k] = {"dram_bytes_per_launch": sum(x[0] for x in v) / len(v), "launches_profiled": len(v),
+            m = lambda j: sum(x[j] for x in v) / len(v)
+            out[k] = {"dram_bytes_per_launch": m(0), "launches_profiled": len(v),
+                      # issue roof of the traversal kernels (bench.py roofline): warp instructions issued, lanes active per instruction, issue slots busy
+                      "warp_inst_per_launch": m(2), "thr_per_inst": m(3), "issue_active_pct": m(4),
                       "source": os.path.basename(rep) + " (ncu --set full, caches flushed before each replay)"}
         json.dump(out, open(sys.argv[2], "w"), indent=1, sort_keys=True)
 

@@ -10,7 +10,7 @@ svo = load_package()
 nfr = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 mode = sys.argv[2] if len(sys.argv) > 2 else "fused"
 path, _ = bench.scene_path()
-bench.make_scene(svo, path)
+bench.make_scene(path)
 octree, root, _ = svo.scene.octree_init(path)
 rc, ocl = svo.raycast, svo.ocl
 rc.raycast_init(octree, root, max_w=1920, max_h=1024, mode=mode)
