@@ -227,6 +227,15 @@ def opencl_probe():
         return f"probe failed: {type(e).__name__}"
 
 
+def host_threads():
+    """Host threads the CPU legs use: the CPUs this process may run on (torchrun exports OMP_NUM_THREADS=1, which would make
+    omp_get_max_threads() say 1; the kernels take an explicit num_threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def oracle_octree(path, depth=11):
     """(lib, kind, octree, root) of the CPU side, built by the CPU side's own loader: the reference's RLE4::load -> set_voxel ->
     convert_tree_blocks when oracle/_ref exists (src/raycast.h:13-46), else the C restatement."""
@@ -242,7 +251,7 @@ def cpu_arm(lib, kind, octree, root, steps, warmup, budget_s, threads=None):
     work-group-parallel on all host threads, the way an OpenCL CPU runtime runs the reference (raycast_proj with its payload
     race: this leg feeds the clock, not the parity check)."""
     from oracle import frame as ofr
-    cores = threads or lib.max_threads()
+    cores = threads or host_threads()
     F = ofr.OracleFrame(lib, octree, root, RES_X, RES_Y, threads=cores, timed=True)
     times = []
     t_start = time.perf_counter()
@@ -299,7 +308,7 @@ def parity_flythrough(svo, lib, octree_cpu, root_cpu, params, nframes, mode):
     from oracle import frame as ofr
     rc = svo.raycast
     n, nb = RES_X * RES_Y, (RES_X // 16) * (RES_Y // 16)
-    O = ofr.OracleFrame(lib, octree_cpu, root_cpu, RES_X, RES_Y, threads=lib.max_threads())
+    O = ofr.OracleFrame(lib, octree_cpu, root_cpu, RES_X, RES_Y, threads=host_threads())
     rc.reset_frames()
     # the coordinate buffers still hold the timed passes' frames; pixels no kernel writes in this pass (stale positions under
     # hole words, w of never-reprojected pixels) are compared too, so both sides start from zeroed memory
@@ -336,7 +345,7 @@ def oracle_full_raycast(lib, octree_cpu, root_cpu, rx, ry, pose, depth=11):
     back = np.zeros(16 * n + 64, dtype=np.float32)
     tex = np.zeros(n, dtype=np.uint32)
     cam = ofr.camera_args(*pose, depth)
-    t = lib.max_threads()
+    t = host_threads()
     lib.raycast_fine_2(screen, back, octree_cpu, root_cpu, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], threads=t, gx=rx, gy=ry)
     lib.raycast_colorize(screen, tex, rx, ry, threads=t)
     return screen[:n], back[:4 * n], tex
@@ -355,7 +364,7 @@ def octree_words_per_ray(octree, root, frames=(0, 40)):
     for f in frames:
         cam = ofr.camera_args(*flythrough_pose(f))
         add_x, add_y = (RES_X // 8) * (f & 7), (RES_Y // 4) * ((f >> 3) & 3)
-        orc.raycast_fine_2(screen, back, octree, root, RES_X, RES_Y, f, add_x, add_y, cam["v0"], *cam["cols"], threads=orc.max_threads())
+        orc.raycast_fine_2(screen, back, octree, root, RES_X, RES_Y, f, add_x, add_y, cam["v0"], *cam["cols"], threads=host_threads())
     r, i, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
     orc.lib.orc_stats(C.byref(r), C.byref(i), C.byref(l))
     return l.value / max(1, r.value), i.value / max(1, r.value)
@@ -450,7 +459,7 @@ def band_bench(svo, octree, root, rank, world, local_rank, dist, torch, args, fr
                 img = db.band.read(B.TEX, np.uint32, n) if rank == 0 else None
                 if rank == 0 and cpu is not None:
                     from oracle import frame as ofr
-                    O = ofr.OracleFrame(cpu[0], cpu[1], cpu[2], RX, RY, threads=cpu[0].max_threads())
+                    O = ofr.OracleFrame(cpu[0], cpu[1], cpu[2], RX, RY, threads=host_threads())
                     for f in range(PARITY_FRAMES):
                         O.draw(*flythrough_pose(f))
                     nb = O.nblocks
@@ -560,7 +569,7 @@ def terrain14_bench(svo, args, frames=64, with_parity=True):
         orc = binding.get("orc")
         orc.lib.orc_set_depth(14)
         try:
-            O = ofr.OracleFrame(orc, octree, root, RES_X, RES_Y, threads=orc.max_threads(), depth=14)
+            O = ofr.OracleFrame(orc, octree, root, RES_X, RES_Y, threads=host_threads(), depth=14)
             nb = O.nblocks
             rc.reset_frames()
             bad = {"image_words": 0, "id_words": 0, "idbuf_size": 0}
@@ -788,6 +797,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(mr, op=dist.ReduceOp.SUM)
+    if world > 1:                                                    # every rank's own device time: is the max one slow rank or all of them?
+        mine = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        ms_ranks = [float(v[0]) for v in allms]
+    else:
+        ms_ranks = [ms]
     e2e_passes_ms = sorted(float(v) for v in t[3:])                  # per pass: max over ranks
     ms_max, e2e_ms_max, cams_ms_max = float(t[0]), e2e_passes_ms[len(e2e_passes_ms) // 2], float(t[2])
     fps = world * args.steps / (ms_max * 1e-3)
@@ -852,7 +868,7 @@ def main():
                 "config": config,
                 "details": {"octree_mb": round(octree.nbytes / 2 ** 20, 1), "voxels": stats["num_voxels"], "mode": args.mode,
                             "parallelism": "1 GPU" if world == 1 else f"view-parallel x{world} ({'a different camera path' if args.distinct_paths else 'the config-2 flythrough'} on every GPU, octree replicated, no communication)",
-                            "hole_fraction_last_frame": hole_frac},
+                            "hole_fraction_last_frame": hole_frac, "ms_per_step_by_rank": [round(v / args.steps, 5) for v in ms_ranks]},
                 "full_raycast_mrays_per_s": float(mr[0]), "full_raycast_ms": float(np.median(ray_ms)),
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus,

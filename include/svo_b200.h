@@ -141,12 +141,12 @@ unsigned long long svo_frame_deferred_count(void);
  * nranks contiguous bands); stripe s belongs to rank s % nranks.  Every rank holds the octree and full-size buffers laid
  * out like the reference's (src/raycast.h:79-85) but owns only its rows.  The frame is the fused frame above with the
  * reprojection's depth test resolved by 64-bit atomicMin straight into the owner's key buffer over NVLink, peer gathers of
- * the winners, colorized rows stored into rank 0's frame, and flag barriers in peer memory; results are bit-identical to
- * one GPU.  One band per context; create the context first (svo_init / svo_ctx_create + svo_ctx_set_current) and
+ * the winners, colorized words stored into rank 0's frame by their producers, the gap filter reading its neighbours' rows by
+ * peer loads, and two flag barriers in peer memory per frame (a third beside the stream); results are bit-identical to one GPU.  One band per context; create the context first (svo_init / svo_ctx_create + svo_ctx_set_current) and
  * svo_malloc the octree in it. */
 typedef struct svo_band_s *svo_band_t;
 enum { SVO_IPC_HANDLE_BYTES = 64, SVO_BAND_MAX_RANKS = 8 };
-typedef struct svo_band_handles { unsigned char mem[6][SVO_IPC_HANDLE_BYTES]; } svo_band_handles;  /* screen back key halo tex flags */
+typedef struct svo_band_handles { unsigned char mem[6][SVO_IPC_HANDLE_BYTES]; } svo_band_handles;  /* screen back key (reserved) tex flags */
 enum { SVO_BAND_SCREEN = 0, SVO_BAND_BACK = 1, SVO_BAND_IDBUF = 2, SVO_BAND_TEX = 3, SVO_BAND_HALO = 4 };
 
 /* pure host arithmetic (no device needed): out = {effective stripe rows, rows owned, whole 16-row block rows owned, stripes owned} */
@@ -175,6 +175,8 @@ int  svo_band_write(svo_band_t band, int which, const void *src, size_t bytes, s
 svo_ctx_t svo_band_ctx(svo_band_t band);
 int  svo_band_last_slot(svo_band_t band);
 void *svo_band_tex_device_ptr(svo_band_t band);
+/* frames of this rank whose scatter carried the previous frame's cache copy (the band form of svo_frame_deferred_count) */
+unsigned long long svo_band_deferred_count(svo_band_t band);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ _band_read = ocl._sig("svo_band_read", _i, _vp, _i, _vp, _sz, _sz)
 _band_write = ocl._sig("svo_band_write", _i, _vp, _i, _vp, _sz, _sz)
 _band_ctx = ocl._sig("svo_band_ctx", _vp, _vp)
 _band_last_slot = ocl._sig("svo_band_last_slot", _i, _vp)
+_band_deferred_count = ocl._sig("svo_band_deferred_count", C.c_ulonglong, _vp)
 
 
 # ---- layout (mirrors svo_band_layout; pure arithmetic) -----------------------------------------------------------
@@ -125,6 +126,10 @@ class Band:
 
     def ctx(self):
         return _band_ctx(self.handle)
+
+    def deferred_count(self):
+        """Frames of this rank whose scatter carried the previous frame's cache copy (svo_band_deferred_count)."""
+        return int(_band_deferred_count(self.handle))
 
     def read(self, which, dtype, count, offset_bytes=0):
         out = np.empty(count, dtype=dtype)

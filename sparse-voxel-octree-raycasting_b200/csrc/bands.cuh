@@ -7,14 +7,22 @@
 //     gives G contiguous bands; a small SR interleaves them (load balance for full raycasts: sky rows are cheap);
 //   * reprojection: every rank projects its own cached rows and resolves the depth test with the same 64-bit
 //     atomicMin (depth | source offset) as one GPU does -- issued straight into the OWNER's key buffer through its peer
-//     mapping (NVLink atomics).  The min is order independent, so the result is the 1-GPU result bit for bit;
-//   * resolve + hole gather: every rank walks its own keys and gathers the winner's colour / position from whichever
-//     rank owns the source row (peer loads); the hole ids of a rank are the 1-GPU id list restricted to its blocks, in
-//     the same order, and feed that rank's own hole raycast;
-//   * cache copy + colorize: own rows; the colorized rows go straight into the writer rank's frame (peer stores), and the
-//     2 + 3 rows the small-gap filter's 5x5 search can reach across a stripe edge are pushed into the neighbour's halo;
-//   * cross-GPU ordering is a flag barrier in peer memory (k_band_barrier, one tiny launch): after the scatter, before the
-//     cache copy (exact mode), before the gap filter, and at the end of the frame.
+//     mapping (NVLink atomics).  The min is order independent, so the result is the 1-GPU result bit for bit.  In steady
+//     state the pass also carries the previous frame's cache copy of the rank's rows (lazy copy, fused.cuh);
+//   * hole ids from the keys alone (k_band_hole_ids), so the rank's hole rays start right behind the exchange; the
+//     resolve / gather pass runs beside them: it walks the rank's own keys and gathers the winner's colour / position from
+//     whichever rank owns the source row (peer loads).  The hole ids of a rank are the 1-GPU id list restricted to its
+//     blocks, in the same order;
+//   * colorize at the producers: gather pass, rays and gap filter store their colorized words straight into the writer
+//     rank's frame (peer stores), there is no colorize pass and no transfer pass;
+//   * the small-gap filter reads the 2 + 3 rows its 5x5 search can reach across a stripe edge straight out of the
+//     neighbour's frame (peer loads; the filter's in-place write is deferred, so the frame stays the pre-filter image);
+//   * cross-GPU ordering is a flag barrier in peer memory (k_band_barrier, one tiny launch).  Two per frame on the critical
+//     stream: B1 after the scatter (every candidate has reached its owner's keys) and B2 after the rays and the gather pass
+//     (nobody gathers from the cache rows or writes the keys any more: the next frame's scatter may overwrite them; the
+//     neighbours' frames are final: the gap filter may read them).  A third, B3, follows the gap filter on its side stream
+//     (second flag set): the writer's frame is complete, and the next frame's gather pass / hole rays -- which rewrite
+//     the frame the neighbours' filters were reading -- wait for it on their streams, never the critical one.
 // No NCCL on the data path; torch.distributed only carries the IPC handles once at start-up.
 #pragma once
 #include "fused.cuh"
@@ -37,11 +45,10 @@ struct BandPeers {                               // base pointers of every rank'
     uint32_t *screen[kMaxBands];
     float *back[kMaxBands];
     unsigned long long *key[kMaxBands];
-    uint32_t *halo[kMaxBands];                   // [local stripe][5][res_x]: 2 rows above, 3 rows below the stripe
     uint32_t *tex;                               // the writer's colorize target
 };
 
-struct BandFlags { uint32_t *of[kMaxBands]; };   // of[p] = rank p's flag words; word r is written by rank r
+struct BandFlags { uint32_t *of[kMaxBands]; };   // of[p] = rank p's flag words: two sets of kMaxBands words (critical stream / gap-filter stream); word r of a set is written by rank r
 
 __device__ __forceinline__ unsigned long long band_globaltimer()
 {
@@ -54,51 +61,175 @@ __device__ __forceinline__ unsigned long long band_globaltimer()
 // and waits until rank p has published it here.  Stream order makes every earlier launch of this rank (and its peer
 // stores / atomics, fenced by their threads) precede the flag.  A rank that never shows up is reported after 2 s
 // instead of hanging the GPU.
-__global__ void k_band_barrier(BandFlags f, int rank, int G, uint32_t epoch, unsigned int *status)
+__global__ void k_band_barrier(BandFlags f, int rank, int G, uint32_t epoch, unsigned int *status, int set)
 {
     const int p = threadIdx.x;
     if (p >= G || p == rank) return;
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.of[p] + rank), "r"(epoch) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.of[p] + set * kMaxBands + rank), "r"(epoch) : "memory");
     const unsigned long long t0 = band_globaltimer();
     for (;;) {
         uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.of[rank] + p) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.of[rank] + set * kMaxBands + p) : "memory");
         if ((int)(v - epoch) >= 0) break;
         if (band_globaltimer() - t0 > 2000000000ull) { atomicExch(status, 1u); break; }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// reprojection scatter (raycast_proj, kernel.cl:472-592): own rows of `nslots` source buffers starting at slot `slot0`
+// reprojection scatter (raycast_proj, kernel.cl:472-592): own rows of `nslots` source buffers starting at slot `slot0`.
+// copy_slot >= 0 (lazy cache copy, see k_proj_scatter2): the single source slot is the frame the rank rendered last; its rows
+// are stored into slot `copy_slot` on the way and the keys name the pixels there (key_bias = copy_slot * N).
 __global__ void __launch_bounds__(256)
-k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int nslots, ProjCam c)
+k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int nslots, int copy_slot,
+               unsigned int key_bias, ProjCam c)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
     // (the reference's "source leaves the view -> hole" store has no reader inside the frame, see k_proj_scatter2)
-    const uint32_t *__restrict__ screen = P.screen[m.rank];
-    const float *__restrict__ back = P.back[m.rank];
+    uint32_t *__restrict__ screen = P.screen[m.rank];
+    float *__restrict__ back = P.back[m.rank];
     const unsigned int n = (unsigned int)m.res_x * m.res_y, nloc = (unsigned int)m.local_rows * m.res_x;
     bool remote = false;
     for (int s = 0; s < nslots; ++s)
         for (unsigned int lp = blockIdx.x * blockDim.x + threadIdx.x; lp < nloc; lp += gridDim.x * blockDim.x) {
             const int lr = (int)(lp / (unsigned int)m.res_x), x = (int)lp - lr * m.res_x;
-            const uint32_t srcofs = (uint32_t)(slot0 + s) * n + (uint32_t)m.global_row(lr) * m.res_x + x;
-            const uint32_t col = screen[srcofs];
+            const uint32_t pix = (uint32_t)m.global_row(lr) * m.res_x + x;
+            const uint32_t srcofs = (uint32_t)(slot0 + s) * n + pix;
+            const uint32_t col = ld_stream(screen + srcofs);
+            float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (copy_slot >= 0 || col != kHole) pc = ld_stream(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
+            if (copy_slot >= 0) {                        // the copy takes every pixel, holes and their stale positions included
+                screen[(size_t)copy_slot * n + pix] = col;
+                *reinterpret_cast<float4 *>(back + ((size_t)copy_slot * n + pix) * 4) = pc;
+            }
             if (col == kHole) continue;
-            const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4);
             int sx, sy; float phz;
             if (!proj_point_fast(c, pc.x, pc.y, pc.z, m.res_x, m.res_y, sx, sy, phz)) continue;
             const int o = m.owner(sy);
             remote |= o != m.rank;
-            atomicMin(P.key[o] + (size_t)sy * m.res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | srcofs);
+            atomicMin(P.key[o] + (size_t)sy * m.res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (srcofs + key_bias));
         }
     if (remote) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The hole index list of this rank's blocks from its keys alone (k_hole_ids of fused.cuh with the band maps): local block
+// b is column b % nbx of the rank's (b / nbx)-th owned block row.  Reads 8 B/pixel, writes the list; what the hole rays wait for.
+__global__ void __launch_bounds__(256)
+k_band_hole_ids(BandMap m, const unsigned long long *__restrict__ key, uint32_t *__restrict__ idb, FusedScratch s, uint32_t epoch)
+{
+    __shared__ unsigned int ticket_s;
+    __shared__ uint32_t warp_cnt[2][8];
+    __shared__ uint32_t cta_prefix_s;
+    const int res_x = m.res_x;
+    const int nbx = res_x / 16, nblocks = nbx * m.local_brows;
+    const int ncta = (nblocks + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) ticket_s = atomicAdd(&s.counters[0], 1u);
+    __syncthreads();
+    const unsigned int ticket = ticket_s;
+    const bool even = (res_x & 1) == 0;
+    bool hole[2] = {false, false}, active[2];
+    int x[2] = {0, 0}, y[2] = {0, 0}, blk[2];
+    unsigned long long k[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        blk[c] = (int)ticket * kIdsBlocksPerCta + c * kGatherBlocksPerCta + (warp >> 1);
+        active[c] = blk[c] < nblocks;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) k[c][i] = kKeyEmpty;
+        if (active[c]) {
+            const int bx = blk[c] % nbx, by = m.global_brow(blk[c] / nbx);
+            x[c] = bx * 16 + (lane & 7) * 2;
+            y[c] = by * 16 + ((warp & 1) * 4 + (lane >> 3)) * 2;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const size_t p = (size_t)(y[c] + r) * res_x + x[c];
+                if (even) {
+                    const ulonglong2 kk = ld_stream(reinterpret_cast<const ulonglong2 *>(key + p));
+                    k[c][2 * r] = kk.x; k[c][2 * r + 1] = kk.y;
+                } else { k[c][2 * r] = ld_stream(key + p); k[c][2 * r + 1] = ld_stream(key + p + 1); }
+            }
+        }
+    }
+    unsigned mk[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        hole[c] = active[c] && !key_valid(k[c][0]) && !key_valid(k[c][1]) && !key_valid(k[c][2]) && !key_valid(k[c][3]);
+        mk[c] = __ballot_sync(0xffffffffu, hole[c]);
+        if (lane == 0) warp_cnt[c][warp] = 4u * (uint32_t)__popc(mk[c]);
+    }
+    __syncthreads();
+    uint32_t cta_total = 0, before_me[2] = {0, 0}, my_cnt[2];
+#pragma unroll
+    for (int j = 0; j < kIdsBlocksPerCta; ++j) {
+        const uint32_t cnt = warp_cnt[j / kGatherBlocksPerCta][2 * (j % kGatherBlocksPerCta)] + warp_cnt[j / kGatherBlocksPerCta][2 * (j % kGatherBlocksPerCta) + 1];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) if (j < c * kGatherBlocksPerCta + (warp >> 1)) before_me[c] += cnt;
+        cta_total += cnt;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) my_cnt[c] = warp_cnt[c][warp & ~1] + warp_cnt[c][warp | 1];
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    if (tid == 0) atomicExch(&s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
+    if (warp == 0) {                                                   // decoupled look-back over the predecessors' aggregates
+        uint32_t excl = 0;
+        if (ticket > 0) {
+            int look = (int)ticket - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long v = 0;
+                if (idx >= 0) {
+                    do { v = *reinterpret_cast<volatile unsigned long long *>(&s.scan_state[idx]); }
+                    while ((v >> 34) != epoch || ((v >> 32) & 3ull) == 0);
+                }
+                const bool is_prefix = idx >= 0 && ((v >> 32) & 3ull) == 2ull;
+                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                uint32_t val = (idx >= 0 && lane <= first) ? (uint32_t)v : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                excl += val;
+                if (pm || look - 32 < 0) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(&s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
+        }
+        if (lane == 0) cta_prefix_s = excl;
+    }
+    __syncthreads();
+    const uint32_t cta_prefix = cta_prefix_s;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (!active[c]) continue;
+        const uint32_t ofs = cta_prefix + before_me[c];
+        if ((warp & 1) == 0 && lane == 0) {
+            if (blk[c] > 0) idb[blk[c]] = my_cnt[c];                   // raycast_counthole :273 (word 0 becomes the total)
+            idb[nblocks + blk[c]] = ofs;                               // raycast_sumids :292
+        }
+        if (hole[c]) {
+            const uint32_t first_half = warp_cnt[c][warp & ~1];
+            const uint32_t rank = (uint32_t)__popc(mk[c] & ((1u << lane) - 1u));
+            uint32_t *o = idb + 2 * (uint32_t)nblocks + ofs + ((warp & 1) ? first_half : 0u) + 4u * rank;
+            const uint32_t val = (uint32_t)x[c] | ((uint32_t)y[c] << 16);  // raycast_writeids :324,:334-337
+            o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
+        }
+    }
+    if (ticket == (unsigned)ncta - 1 && tid == 0) idb[0] = cta_prefix + cta_total;   // raycast_sumids :295
+    __syncthreads();
+    if (tid == 0) {                                                    // the last CTA to finish re-arms the ticket counters
+        __threadfence();
+        const unsigned int done = atomicAdd(&s.counters[1], 1u);
+        if (done == gridDim.x - 1) { s.counters[0] = 0; s.counters[1] = 0; __threadfence(); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 struct BandGatherArgs {
-    BandMap m; BandPeers P; uint32_t *idb; FusedScratch s; uint32_t epoch; int dst_slot; ProjCam c;
+    BandMap m; BandPeers P; FusedScratch s; int dst_slot; ProjCam c;
+    Rect tile;                               // the tile-refresh rectangle: its colour / xyz come from the staging buffers
+    const uint32_t *stage_s; const float *stage_b;
+    uint32_t *tex;                           // the writer's frame (peer mapping on ranks != 0)
 };
 
 __device__ __forceinline__ void band_source(const BandMap &m, const BandPeers &P, uint32_t srcofs, uint32_t n,
@@ -107,17 +238,50 @@ __device__ __forceinline__ void band_source(const BandMap &m, const BandPeers &P
     uint32_t p = srcofs;
     while (p >= n) p -= n;
     const int o = m.owner((int)(p / (uint32_t)m.res_x));
-    col = P.screen[o][srcofs];
-    pc = *reinterpret_cast<const float4 *>(P.back[o] + (size_t)srcofs * 4);
+    col = ld_stream(P.screen[o] + srcofs);
+    pc = ld_stream(reinterpret_cast<const float4 *>(P.back[o] + (size_t)srcofs * 4));
 }
 
-// clear + depth-test resolve + hole gather of this rank's blocks (k_resolve_gather of fused.cuh with the band maps)
-__global__ void __launch_bounds__(256)
-k_band_resolve_gather(const BandGatherArgs a)
+// One pixel outside the 2x2 hole cells' reach (the right / bottom strips): resolve only.
+__device__ __forceinline__ void band_gather_strip_pixel(const BandGatherArgs &a, unsigned long long *key, uint32_t *dscreen, float *dback,
+                                                         uint32_t n, int x, int y)
 {
-    __shared__ unsigned int ticket_s;
-    __shared__ uint32_t warp_cnt[8];
-    __shared__ uint32_t cta_prefix_s;
+    const BandMap &m = a.m;
+    const size_t p = (size_t)y * m.res_x + x;
+    const unsigned long long k = key[p];
+    if (k != kKeyEmpty) key[p] = kKeyEmpty;
+    const bool v = key_valid(k), inr = in_rect(a.tile, x, y);
+    if (inr) {                                                           // the tile ray's result, staged
+        const uint32_t w = a.stage_s[p];
+        dscreen[p] = w;
+        a.tex[p] = colorize_word(w);
+        dback[p * 4] = a.stage_b[p * 4]; dback[p * 4 + 1] = a.stage_b[p * 4 + 1]; dback[p * 4 + 2] = a.stage_b[p * 4 + 2];
+    }
+    if (v) {
+        uint32_t col; float4 pc;
+        band_source(m, a.P, (uint32_t)k, n, col, pc);
+        const float phz = (pc.x - a.c.m0x) * a.c.mzx + (pc.y - a.c.m0y) * a.c.mzy + (pc.z - a.c.m0z) * a.c.mzz;
+        if (inr) dback[p * 4 + 3] = phz;
+        else {
+            const uint32_t w = (uint32_t)(k >> 32) + (col & 255u);
+            dscreen[p] = w;
+            a.tex[p] = colorize_word(w);
+            *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz);
+        }
+    } else if (!inr) {
+        dscreen[p] = kHole;
+        a.tex[p] = colorize_word(kHole);
+        if (x > 1 && y > 1 && x < m.res_x - 1 && y < m.res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
+    }
+}
+
+// clear + depth-test resolve + gather + destination + colorized words + gap-filter list of this rank's blocks
+// (k_resolve_gather<false> of fused.cuh with the band maps): runs beside the rank's hole rays and writes nothing into the 2x2
+// cells they fill.  Winners are gathered from whichever rank owns the source row (peer loads), colorized words go to the
+// writer's frame (peer stores).
+__global__ void __launch_bounds__(256)
+k_band_gather(const BandGatherArgs a)
+{
     __shared__ unsigned int resid_cta_s, resid_base_s;
     const BandMap &m = a.m;
     const int res_x = m.res_x, res_y = m.res_y;
@@ -128,41 +292,27 @@ k_band_resolve_gather(const BandGatherArgs a)
     unsigned long long *__restrict__ key = a.P.key[m.rank];
     uint32_t *__restrict__ dscreen = a.P.screen[m.rank] + (size_t)a.dst_slot * n;
     float *__restrict__ dback = a.P.back[m.rank] + (size_t)a.dst_slot * n * 4;
-    if (tid == 0) ticket_s = atomicAdd(&a.s.counters[0], 1u);
-    __syncthreads();
-    const unsigned int ticket = ticket_s;
+    const int ticket = blockIdx.x;
 
-    if (ticket >= (unsigned)ncta) {
+    if (ticket >= ncta) {
         // pixels outside the whole 16x16 blocks: right strip of the owned block rows, bottom strip if this rank owns it
-        const int strip_cta = (int)ticket - ncta;
+        const int strip_cta = ticket - ncta;
         const int wx = nbx * 16, wy = nby * 16;
         const int n_right = (res_x - wx) * m.local_brows * 16;
         const int n_bottom = (wy < res_y && m.owner(wy) == m.rank) ? res_x * (res_y - wy) : 0;
-        for (int i = strip_cta * 256 + tid; i < n_right + n_bottom; i += (gridDim.x - ncta) * 256) {
+        for (int i = strip_cta * 256 + tid; i < n_right + n_bottom; i += ((int)gridDim.x - ncta) * 256) {
             int x, y;
             if (i < n_right) { x = wx + i % (res_x - wx); y = m.global_row(i / (res_x - wx)); }
             else { const int j = i - n_right; x = j % res_x; y = wy + j / res_x; }
-            const size_t p = (size_t)y * res_x + x;
-            const unsigned long long k = key[p];
-            if (k != kKeyEmpty) key[p] = kKeyEmpty;
-            if (key_valid(k)) {
-                uint32_t col; float4 pc;
-                band_source(m, a.P, (uint32_t)k, n, col, pc);
-                const float phz = (pc.x - a.c.m0x) * a.c.mzx + (pc.y - a.c.m0y) * a.c.mzy + (pc.z - a.c.m0z) * a.c.mzz;
-                dscreen[p] = (uint32_t)(k >> 32) + (col & 255u);
-                *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz);
-            } else {
-                dscreen[p] = kHole;
-                if (x > 1 && y > 1 && x < res_x - 1 && y < res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
-            }
+            band_gather_strip_pixel(a, key, dscreen, dback, n, x, y);
         }
     } else {
-        const int b = (int)ticket * kGatherBlocksPerCta + (warp >> 1);      // local block index
+        const int b = ticket * kGatherBlocksPerCta + (warp >> 1);          // local block index
         const bool active = b < nblocks;
         const bool even = (res_x & 1) == 0;
         bool hole = false;
         int x = 0, y = 0;
-        bool valid[4] = {false, false, false, false};
+        bool valid[4] = {false, false, false, false}, inr[4] = {false, false, false, false};
         size_t pp[2] = {0, 0};
         unsigned long long k[4] = {kKeyEmpty, kKeyEmpty, kKeyEmpty, kKeyEmpty};
         if (active) {
@@ -174,36 +324,33 @@ k_band_resolve_gather(const BandGatherArgs a)
                 const size_t p = (size_t)(y + r) * res_x + x;
                 pp[r] = p;
                 if (even) {
-                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(key + p);
+                    const ulonglong2 kk = ld_stream(reinterpret_cast<const ulonglong2 *>(key + p));
                     k[2 * r] = kk.x; k[2 * r + 1] = kk.y;
-                } else { k[2 * r] = key[p]; k[2 * r + 1] = key[p + 1]; }
+                } else { k[2 * r] = ld_stream(key + p); k[2 * r + 1] = ld_stream(key + p + 1); }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) valid[i] = key_valid(k[i]);
             hole = !valid[0] && !valid[1] && !valid[2] && !valid[3];
         }
-        // aggregate published before the (possibly remote) gathers, as in k_resolve_gather
-        const unsigned mk = __ballot_sync(0xffffffffu, hole);
-        if (lane == 0) warp_cnt[warp] = 4u * (uint32_t)__popc(mk);
         if (tid == 0) resid_cta_s = 0;
         __syncthreads();
-        uint32_t cta_total = 0, before_me = 0;
-#pragma unroll
-        for (int i = 0; i < kGatherBlocksPerCta; ++i) {
-            const uint32_t cnt = warp_cnt[2 * i] + warp_cnt[2 * i + 1];
-            if (i < (warp >> 1)) before_me += cnt;
-            cta_total += cnt;
-        }
-        const uint32_t my_block_cnt = warp_cnt[warp & ~1] + warp_cnt[warp | 1];
-        const unsigned long long tag = (unsigned long long)a.epoch << 34;
-        if (tid == 0) atomicExch(&a.s.scan_state[ticket], tag | ((ticket == 0 ? 2ull : 1ull) << 32) | cta_total);
-
         if (active) {
             uint32_t col[4]; float4 pc[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i) {                                   // all four (possibly remote) gathers in flight
+                inr[i] = in_rect(a.tile, x + (i & 1), y + (i >> 1));
                 col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid[i]) band_source(m, a.P, (uint32_t)k[i], n, col[i], pc[i]);
+            }
+            uint32_t scol[4] = {0, 0, 0, 0}; float4 spc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inr[i] && !hole) {
+                    const size_t q = pp[i >> 1] + (i & 1);
+                    scol[i] = ld_stream(a.stage_s + q);
+                    spc[i] = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + q * 4));      // w unused
+                }
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -220,19 +367,32 @@ k_band_resolve_gather(const BandGatherArgs a)
                     if (valid[i]) {
                         const float phz = (pc[i].x - a.c.m0x) * a.c.mzx + (pc[i].y - a.c.m0y) * a.c.mzy + (pc[i].z - a.c.m0z) * a.c.mzz;
                         out[j] = (uint32_t)(k[i] >> 32) + (col[i] & 255u);
-                        *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
+                        if (inr[i]) dback[(p + j) * 4 + 3] = phz;                 // the tile ray supplies colour and xyz, never w
+                        else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
+                    }
+                    if (inr[i] && !hole) {                                       // ... from the staging buffers
+                        out[j] = scol[i];
+                        *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc[i].x, spc[i].y);
+                        dback[(p + j) * 4 + 2] = spc[i].z;
                     }
                 }
-                if (even) *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
-                else { dscreen[p] = out[0]; dscreen[p + 1] = out[1]; }
+                if (hole) continue;                                              // the hole rays own this cell
+                if (even) {
+                    *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
+                    *reinterpret_cast<uint2 *>(a.tex + p) = make_uint2(colorize_word(out[0]), colorize_word(out[1]));
+                } else {
+                    dscreen[p] = out[0]; a.tex[p] = colorize_word(out[0]);
+                    dscreen[p + 1] = out[1]; a.tex[p + 1] = colorize_word(out[1]);
+                }
             }
         }
+        // hole pixels that no ray will fill -> gap-filter list (bounds of kernel.cl:416), one global atomic per CTA
         unsigned int rflags = 0;
         if (active && !hole) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int px = x + (i & 1), py = y + (i >> 1);
-                if (!valid[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
+                if (!valid[i] && !inr[i] && px > 1 && py > 1 && px < res_x - 1 && py < res_y - 1) rflags |= 1u << i;
             }
         }
         const unsigned int rcnt = (unsigned int)__popc(rflags);
@@ -240,84 +400,39 @@ k_band_resolve_gather(const BandGatherArgs a)
         if (rcnt) rofs = atomicAdd(&resid_cta_s, rcnt);
         __syncthreads();
         if (tid == 0) resid_base_s = resid_cta_s ? atomicAdd(a.s.resid_count, resid_cta_s) : 0u;
-        if (warp == 0) {                                                    // decoupled look-back, as in k_resolve_gather
-            uint32_t excl = 0;
-            if (ticket > 0) {
-                int look = (int)ticket - 1;
-                while (true) {
-                    const int idx = look - lane;
-                    unsigned long long v = 0;
-                    if (idx >= 0) {
-                        do { v = *reinterpret_cast<volatile unsigned long long *>(&a.s.scan_state[idx]); }
-                        while ((v >> 34) != a.epoch || ((v >> 32) & 3ull) == 0);
-                    }
-                    const bool is_prefix = idx >= 0 && ((v >> 32) & 3ull) == 2ull;
-                    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                    const int first = pm ? __ffs(pm) - 1 : 31;
-                    uint32_t val = (idx >= 0 && lane <= first) ? (uint32_t)v : 0u;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                    excl += val;
-                    if (pm || look - 32 < 0) break;
-                    look -= 32;
-                }
-                if (lane == 0) atomicExch(&a.s.scan_state[ticket], tag | (2ull << 32) | (unsigned long long)(excl + cta_total));
-            }
-            if (lane == 0) cta_prefix_s = excl;
-        }
         __syncthreads();
         if (rflags) {
             uint32_t *o = a.s.resid + resid_base_s + rofs;
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
         }
-        const uint32_t cta_prefix = cta_prefix_s;
-        if (active) {
-            const uint32_t ofs = cta_prefix + before_me;
-            if ((warp & 1) == 0 && lane == 0) {
-                if (b > 0) a.idb[b] = my_block_cnt;
-                a.idb[nblocks + b] = ofs;
-            }
-            if (hole) {
-                const uint32_t first_half = warp_cnt[warp & ~1];
-                const uint32_t rank = (uint32_t)__popc(mk & ((1u << lane) - 1u));
-                uint32_t *o = a.idb + 2 * (uint32_t)nblocks + ofs + ((warp & 1) ? first_half : 0u) + 4u * rank;
-                const uint32_t val = (uint32_t)x | ((uint32_t)y << 16);
-                o[0] = val; o[1] = val + 1u; o[2] = val + 1u + (1u << 16); o[3] = val + (1u << 16);
-            }
-        }
-        if (ticket == (unsigned)ncta - 1 && tid == 0) a.idb[0] = cta_prefix + cta_total;
     }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int done = atomicAdd(&a.s.counters[1], 1u);
-        if (done == gridDim.x - 1) {
-            if (ncta == 0) a.idb[0] = 0;                                    // a rank without whole blocks has no hole rays
-            a.s.counters[0] = 0; a.s.counters[1] = 0; __threadfence();
-        }
-    }
+    if (m.rank != 0) __threadfence_system();                                // colorized words stored into the writer's frame
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// hole rays of this rank's id list (idsize = its block count)
+// hole rays of this rank's id list (idsize = its block count); colorized words go straight into the writer's frame
 template <int D>
 __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
-                  const uint32_t *__restrict__ idb, int idsize, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs)
+                  const uint32_t *__restrict__ idb, int idsize, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs, int remote_tex)
 {
     __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     const long long total = (long long)idb[0];
     const long long nthreads = (long long)gridDim.x * kRaysBlock;
-    const int S = total * 4 <= nthreads ? 4 : total * 2 <= nthreads ? 2 : 1;
+    int S = 1;                                         // lane stride: every S-th lane takes a ray while the grid has room (k_rays_holes)
+    while (S < 8 && total * (S * 2) <= nthreads) S *= 2;
     const long long gtid = (long long)blockIdx.x * kRaysBlock + threadIdx.x;
     if (gtid % S) return;
+    bool wrote = false;
     for (long long w = gtid / S; w < total; w += nthreads / S) {
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        wrote = true;
     }
+    if (wrote && remote_tex) __threadfence_system();
 }
 
 // rays for the owned rows of the rectangle [x0, x0+gx) x [y0, y0+gy) clipped to the screen, 8x4 footprints per warp:
@@ -341,107 +456,80 @@ k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const 
         if (idy < add_y || idy >= add_y + gy || idx >= m.res_x || idy >= m.res_y) continue;
         trace_pixel<D, kRaysBlock, STRAIGHT>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
+    if (fs.tex && m.rank != 0) __threadfence_system();                 // colorized words stored into the writer's frame
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cache copy (exact mode) + colorize of the owned rows; colorized rows -> the writer's frame; stripe-edge rows -> the
-// neighbouring ranks' halos (input of their gap filter)
+// The plain cache copy of the owned rows (src/raycast.h:394-405), issued only when the host observes the rank's buffers
+// before the next frame's scatter has carried it (svo_band_read / svo_band_write); purely local.
 __global__ void __launch_bounds__(256)
-k_band_copy_colorize(BandMap m, BandPeers P, int src_slot, int copy_slot /* -1: no cache copy */, int write_tex, int push_halo)
+k_band_copy(BandMap m, BandPeers P, int src_slot, int copy_slot)
 {
     const int res_x = m.res_x;
     const size_t n = (size_t)res_x * m.res_y;
     const uint32_t *__restrict__ src_s = P.screen[m.rank] + (size_t)src_slot * n;
     const float4 *__restrict__ src_b = reinterpret_cast<const float4 *>(P.back[m.rank]) + (size_t)src_slot * n;
-    uint32_t *__restrict__ dst_s = copy_slot >= 0 ? P.screen[m.rank] + (size_t)copy_slot * n : nullptr;
-    float4 *__restrict__ dst_b = copy_slot >= 0 ? reinterpret_cast<float4 *>(P.back[m.rank]) + (size_t)copy_slot * n : nullptr;
+    uint32_t *__restrict__ dst_s = P.screen[m.rank] + (size_t)copy_slot * n;
+    float4 *__restrict__ dst_b = reinterpret_cast<float4 *>(P.back[m.rank]) + (size_t)copy_slot * n;
     const bool vec = (res_x & 3) == 0;
     const int qpr = vec ? res_x >> 2 : res_x;                       // work items per row (4 pixels or 1)
-    const int nstripes = (m.res_y + m.SR - 1) / m.SR;
     const int total = m.local_rows * qpr;
-    bool remote = false;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         const int lr = q / qpr, xq = q - lr * qpr;
-        const int y = m.global_row(lr);
-        const int x = vec ? xq * 4 : xq;
-        const size_t p = (size_t)y * res_x + x;
-        // halo target of this row (G > 1): the last 2 rows of a stripe are rows "above" the next stripe, the first 3 rows
-        // are rows "below" the previous one
-        uint32_t *halo = nullptr;
-        if (push_halo && m.G > 1) {
-            const int s = y / m.SR, j = y - s * m.SR;
-            if (j < 3 && s > 0) halo = P.halo[(s - 1) % m.G] + ((size_t)((s - 1) / m.G) * 5 + 2 + j) * res_x + x;
-            else if (j >= m.SR - 2 && s + 1 < nstripes) halo = P.halo[(s + 1) % m.G] + ((size_t)((s + 1) / m.G) * 5 + (j - (m.SR - 2))) * res_x + x;
-        }
+        const size_t p = (size_t)m.global_row(lr) * res_x + (vec ? xq * 4 : xq);
         if (vec) {
             const uint4 v = *reinterpret_cast<const uint4 *>(src_s + p);
-            if (dst_s) {
-                const float4 b0 = src_b[p], b1 = src_b[p + 1], b2 = src_b[p + 2], b3 = src_b[p + 3];
-                *reinterpret_cast<uint4 *>(dst_s + p) = v;
-                dst_b[p] = b0; dst_b[p + 1] = b1; dst_b[p + 2] = b2; dst_b[p + 3] = b3;
-            }
-            if (write_tex) *reinterpret_cast<uint4 *>(P.tex + p) = make_uint4(colorize_word(v.x), colorize_word(v.y), colorize_word(v.z), colorize_word(v.w));
-            if (halo) { *reinterpret_cast<uint4 *>(halo) = v; remote = true; }
-        } else {
-            const uint32_t v = src_s[p];
-            if (dst_s) { dst_s[p] = v; dst_b[p] = src_b[p]; }
-            if (write_tex) P.tex[p] = colorize_word(v);
-            if (halo) { *halo = v; remote = true; }
-        }
+            const float4 b0 = src_b[p], b1 = src_b[p + 1], b2 = src_b[p + 2], b3 = src_b[p + 3];
+            *reinterpret_cast<uint4 *>(dst_s + p) = v;
+            dst_b[p] = b0; dst_b[p + 1] = b1; dst_b[p + 2] = b2; dst_b[p + 3] = b3;
+        } else { dst_s[p] = src_s[p]; dst_b[p] = src_b[p]; }
     }
-    if (remote || (write_tex && m.rank != 0)) __threadfence_system();
 }
 
-// gap filter (raycast_fillhole2) on the listed pixels of this rank: the pre-filter image of owned rows is `snap`
-// (exact: the cache copy; ping-pong: the destination slot), rows of other ranks come from the halo, offsets past the
-// image from `beyond` (the words that follow the image in the reference's layout)
+// gap filter (raycast_fillhole2) on the listed pixels of this rank, snapshot semantics: every rank's destination slot holds
+// the pre-filter image of its rows until the next frame's gather pass (the filter's in-place write is deferred), so rows
+// of other ranks -- the 5x5 search reaches 2 rows above and 3 below a stripe -- are read straight from their owner
+// (peer loads); offsets past the image read the words that follow it in the reference's layout (`beyond`).
 struct BandSnapView {
-    const uint32_t *snap, *beyond, *halo; BandMap m; int n, py;
+    const BandPeers *P; BandMap m; size_t slot_ofs; int n;
     __device__ __forceinline__ uint32_t operator[](int i) const
     {
-        if (i >= n) return beyond[i];
-        const int row = i / m.res_x;
-        if (m.G == 1 || m.owner(row) == m.rank) return snap[i];
-        const int s = py / m.SR, k = s / m.G;
-        const int slot = row < s * m.SR ? row - (s * m.SR - 2) : 2 + row - (s + 1) * m.SR;
-        return halo[((size_t)k * 5 + slot) * m.res_x + (i - row * m.res_x)];
+        if (i >= n) return P->screen[m.rank][slot_ofs + i];
+        return P->screen[m.owner(i / m.res_x)][slot_ofs + i];
     }
 };
 
-__device__ __forceinline__ uint32_t band_fillhole2(const BandSnapView &s, int ofs, int res_x)
-{
-    const uint32_t c1 = s[ofs + 1], c2 = s[ofs - 1], c3 = s[ofs + res_x], c4 = s[ofs - res_x];
-    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
-        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
-    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
-    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
-    uint32_t col = c1;
-    if (col == kHole) col = c3;
-    if (col == kHole) col = s[ofs + 1 + res_x];
-    if (col == kHole)
-        for (int i = -2; i < 3 && col == kHole; ++i)
-            for (int j = -2; j < 3; ++j) {
-                if (col != kHole) break;
-                col = s[ofs + i + j * res_x];
-            }
-    return col;
-}
-
 __global__ void __launch_bounds__(256)
-k_band_fill_list(BandMap m, const uint32_t *__restrict__ snap, const uint32_t *__restrict__ beyond, const uint32_t *__restrict__ halo,
-                 uint32_t *__restrict__ out_s, uint32_t *__restrict__ tex, const FusedScratch s)
+k_band_fill_list(BandMap m, BandPeers P, int dst_slot, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid,
+                 const unsigned int *__restrict__ resid_count, PatchList patch)
 {
-    const unsigned int cnt = s.resid_count[0];
+    const unsigned int cnt = resid_count[0];
     const int n = m.res_x * m.res_y;
+    const BandSnapView view = {&P, m, (size_t)dst_slot * n, n};
+    const uint32_t *__restrict__ own = P.screen[m.rank] + (size_t)dst_slot * n;
     bool wrote = false;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const int p = (int)s.resid[i];
-        if (snap[p] != kHole) continue;
-        const BandSnapView view = {snap, beyond, halo, m, n, p / m.res_x};
-        const uint32_t f = band_fillhole2(view, p, m.res_x);
-        if (f == kHole) continue;
-        if (out_s) out_s[p] = f;
-        if (tex) { tex[p] = colorize_word(f); wrote = true; }
+        const int p = (int)resid[i];
+        if (own[p] != kHole) continue;                   // listed before a ray filled it
+        const uint32_t c1 = view[p + 1], c2 = view[p - 1], c3 = view[p + m.res_x], c4 = view[p - m.res_x];
+        uint32_t f;
+        if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
+            f = (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
+        else if (c1 != kHole && c2 != kHole) f = (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
+        else if (c3 != kHole && c4 != kHole) f = (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+        else {
+            f = c1;                                      // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
+            if (f == kHole) f = c3;
+            if (f == kHole) f = view[p + 1 + m.res_x];
+            if (f == kHole)                              // 5x5 search, x offset outer / y offset inner (:461-467)
+                for (int a = -2; a < 3 && f == kHole; ++a)
+                    for (int b = -2; b < 3; ++b) {
+                        if (f != kHole) break;
+                        f = view[p + a + b * m.res_x];
+                    }
+        }
+        patch.value[p] = f;
+        if (f != kHole) { tex[p] = colorize_word(f); wrote = true; }
     }
     if (wrote && m.rank != 0) __threadfence_system();
 }

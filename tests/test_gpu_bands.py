@@ -83,6 +83,43 @@ def test_band_frames_match_oracle(svo, orc, world, real, G, sr, res, nframes):
 
 
 @pytest.mark.parametrize("real", [False, True], ids=["virtual", "multi-gpu"])
+@pytest.mark.parametrize("pingpong", [False, True], ids=["exact", "pingpong"])
+@pytest.mark.parametrize("G,sr,res,nframes", [(1, 0, (320, 192), 40), (2, 16, (320, 192), 40), (4, 32, (200, 120), 9), (2, 64, (1920, 1024), 6)])
+def test_band_frames_back_to_back(svo, orc, world, real, pingpong, G, sr, res, nframes):
+    """The schedule the bench runs: frames enqueued back to back on every rank with nothing observed in between -- the scatter
+    carries the previous frame's cache copy, the gap filter runs beside the next frame, the filter's in-place write and the
+    last copy are issued only when the buffers are read at the end.  Everything must still be the reference's, bit for bit."""
+    octree, root = world
+    rx, ry = res
+    n = rx * ry
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4)
+    bs = svo.bands.LocalBandSet(devices_for(svo, G, real), octree, root, rx, ry, stripe_rows=sr)
+    try:
+        for f in range(nframes):
+            O.draw(*pose(f))
+            bs.frame(frame_params(svo, rx, ry, f, pingpong=pingpong), sync=False)
+        bs.sync()
+        if not pingpong:
+            assert all(b.deferred_count() == nframes - 2 for b in bs.bands), [b.deferred_count() for b in bs.bands]
+        assert np.array_equal(bs.frame_image(), O.tex), "tex"
+        check_ids(bs, O)
+        screen, back = bs.assemble()
+        if pingpong:
+            slot = bs.bands[0].last_slot()
+            assert np.array_equal(screen[slot * n:(slot + 1) * n], O.screen[2 * n:3 * n]), "colour"
+            got = back[slot * 4 * n:(slot + 1) * 4 * n].view(np.uint32).reshape(n, 4)
+            exp = O.back[8 * n:12 * n].view(np.uint32).reshape(n, 4)
+            live = O.screen[2 * n:3 * n] != HOLE
+            assert np.array_equal(got[live, :3], exp[live, :3]), "xyz"
+        else:
+            assert np.array_equal(screen, O.screen[:4 * n]), "colour"
+            assert np.array_equal(back.view(np.uint32), O.back[:16 * n].view(np.uint32)), "xyz"
+    finally:
+        svo.raycast.S.mode = "fused"
+        bs.close()
+
+
+@pytest.mark.parametrize("real", [False, True], ids=["virtual", "multi-gpu"])
 @pytest.mark.parametrize("G,sr,res,nframes", [(2, 0, (320, 192), 12), (4, 16, (320, 192), 34)])
 def test_band_frames_pingpong(svo, orc, world, real, G, sr, res, nframes):
     """SVO_FRAME_PINGPONG across bands: ids and the colorized frame are the reference's, the slot rendered into holds the
