@@ -80,36 +80,55 @@ __global__ void k_band_barrier(BandFlags f, int rank, int G, uint32_t epoch, uns
 // reprojection scatter (raycast_proj, kernel.cl:472-592): own rows of `nslots` source buffers starting at slot `slot0`.
 // copy_slot >= 0 (lazy cache copy, see k_proj_scatter2): the single source slot is the frame the rank rendered last; its rows
 // are stored into slot `copy_slot` on the way and the keys name the pixels there (key_bias = copy_slot * N).
+// Launch: grid (row quads / 256, owned rows, nslots).  A thread takes four consecutive pixels of one row (res_x % 4 == 0;
+// otherwise one): at 3840x2160 the buffers are far beyond the L2, so the pass is HBM-bound and wants 80 bytes in flight per
+// thread -- the colour words as one uint4, the positions as four float4, all issued before the first use -- and no integer
+// division per pixel.  Remote candidates are plain fire-and-forget reductions on the owner's key (NVLink atomics); the
+// launch boundary plus the barrier's system-scope release order them before any rank reads its keys.
+// (Tried: the barrier behind this pass folded into the kernels on either side of it -- the last CTA here signals, every CTA of
+// the id pass waits in its prologue.  It saves a launch and loses 10 % of the frame at 2 GPUs: the waiting grid holds the SMs'
+// CTA slots, the gap filter of the previous frame starves on its low-priority stream, and every rank's hole rays wait for it.)
 __global__ void __launch_bounds__(256)
-k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int nslots, int copy_slot,
+k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int copy_slot,
                unsigned int key_bias, ProjCam c)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) next_resid_count[0] = 0;
     // (the reference's "source leaves the view -> hole" store has no reader inside the frame, see k_proj_scatter2)
     uint32_t *__restrict__ screen = P.screen[m.rank];
     float *__restrict__ back = P.back[m.rank];
-    const unsigned int n = (unsigned int)m.res_x * m.res_y, nloc = (unsigned int)m.local_rows * m.res_x;
-    bool remote = false;
-    for (int s = 0; s < nslots; ++s)
-        for (unsigned int lp = blockIdx.x * blockDim.x + threadIdx.x; lp < nloc; lp += gridDim.x * blockDim.x) {
-            const int lr = (int)(lp / (unsigned int)m.res_x), x = (int)lp - lr * m.res_x;
-            const uint32_t pix = (uint32_t)m.global_row(lr) * m.res_x + x;
-            const uint32_t srcofs = (uint32_t)(slot0 + s) * n + pix;
-            const uint32_t col = ld_stream(screen + srcofs);
-            float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (copy_slot >= 0 || col != kHole) pc = ld_stream(reinterpret_cast<const float4 *>(back + (size_t)srcofs * 4));
-            if (copy_slot >= 0) {                        // the copy takes every pixel, holes and their stale positions included
-                screen[(size_t)copy_slot * n + pix] = col;
-                *reinterpret_cast<float4 *>(back + ((size_t)copy_slot * n + pix) * 4) = pc;
-            }
-            if (col == kHole) continue;
-            int sx, sy; float phz;
-            if (!proj_point_fast(c, pc.x, pc.y, pc.z, m.res_x, m.res_y, sx, sy, phz)) continue;
-            const int o = m.owner(sy);
-            remote |= o != m.rank;
-            atomicMin(P.key[o] + (size_t)sy * m.res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (srcofs + key_bias));
-        }
-    if (remote) __threadfence_system();
+    const unsigned int n = (unsigned int)m.res_x * m.res_y;
+    const bool vec = (m.res_x & 3) == 0;
+    const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = vec ? xq * 4 : xq;
+    if (x >= m.res_x) return;
+    const uint32_t pix = (uint32_t)m.global_row((int)blockIdx.y) * m.res_x + x;
+    const uint32_t srcofs = (uint32_t)(slot0 + (int)blockIdx.z) * n + pix;
+    uint32_t col[4] = {kHole, kHole, kHole, kHole};
+    float4 pc[4];
+    const int cnt = vec ? 4 : 1;
+    if (vec) {
+        const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(screen + srcofs));
+        col[0] = v.x; col[1] = v.y; col[2] = v.z; col[3] = v.w;
+    } else col[0] = ld_stream(screen + srcofs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < cnt && (copy_slot >= 0 || col[i] != kHole)) pc[i] = ld_stream(reinterpret_cast<const float4 *>(back + (size_t)(srcofs + i) * 4));
+    }
+    if (copy_slot >= 0) {                                // the copy takes every pixel, holes and their stale positions included
+        const size_t d = (size_t)copy_slot * n + pix;
+        if (vec) *reinterpret_cast<uint4 *>(screen + d) = make_uint4(col[0], col[1], col[2], col[3]);
+        else screen[d] = col[0];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < cnt) *reinterpret_cast<float4 *>(back + (d + i) * 4) = pc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i >= cnt || col[i] == kHole) continue;
+        int sx, sy; float phz;
+        if (!proj_point_fast(c, pc[i].x, pc[i].y, pc[i].z, m.res_x, m.res_y, sx, sy, phz)) continue;
+        atomicMin(P.key[m.owner(sy)] + (size_t)sy * m.res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (srcofs + i + key_bias));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -227,9 +246,8 @@ k_band_hole_ids(BandMap m, const unsigned long long *__restrict__ key, uint32_t 
 // ---------------------------------------------------------------------------------------------------------
 struct BandGatherArgs {
     BandMap m; BandPeers P; FusedScratch s; int dst_slot; ProjCam c;
-    Rect tile;                               // the tile-refresh rectangle: its colour / xyz come from the staging buffers
-    const uint32_t *stage_s; const float *stage_b;
-    uint32_t *tex;                           // the writer's frame (peer mapping on ranks != 0)
+    Rect tile;                               // the tile-refresh rectangle: colour / xyz / image there are the tile rays' (k_band_tile_move); only w is written
+    uint32_t *tex;                           // the rank's own image rows
 };
 
 __device__ __forceinline__ void band_source(const BandMap &m, const BandPeers &P, uint32_t srcofs, uint32_t n,
@@ -251,12 +269,6 @@ __device__ __forceinline__ void band_gather_strip_pixel(const BandGatherArgs &a,
     const unsigned long long k = key[p];
     if (k != kKeyEmpty) key[p] = kKeyEmpty;
     const bool v = key_valid(k), inr = in_rect(a.tile, x, y);
-    if (inr) {                                                           // the tile ray's result, staged
-        const uint32_t w = a.stage_s[p];
-        dscreen[p] = w;
-        a.tex[p] = colorize_word(w);
-        dback[p * 4] = a.stage_b[p * 4]; dback[p * 4 + 1] = a.stage_b[p * 4 + 1]; dback[p * 4 + 2] = a.stage_b[p * 4 + 2];
-    }
     if (v) {
         uint32_t col; float4 pc;
         band_source(m, a.P, (uint32_t)k, n, col, pc);
@@ -277,8 +289,8 @@ __device__ __forceinline__ void band_gather_strip_pixel(const BandGatherArgs &a,
 
 // clear + depth-test resolve + gather + destination + colorized words + gap-filter list of this rank's blocks
 // (k_resolve_gather<false> of fused.cuh with the band maps): runs beside the rank's hole rays and writes nothing into the 2x2
-// cells they fill.  Winners are gathered from whichever rank owns the source row (peer loads), colorized words go to the
-// writer's frame (peer stores).
+// cells they fill.  Winners are gathered from whichever rank owns the source row (peer loads); colorized words go to the
+// rank's own image rows, which a copy-engine transfer moves into the writer's frame after the gap filter.
 __global__ void __launch_bounds__(256)
 k_band_gather(const BandGatherArgs a)
 {
@@ -342,16 +354,6 @@ k_band_gather(const BandGatherArgs a)
                 col[i] = 0; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid[i]) band_source(m, a.P, (uint32_t)k[i], n, col[i], pc[i]);
             }
-            uint32_t scol[4] = {0, 0, 0, 0}; float4 spc[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (inr[i] && !hole) {
-                    const size_t q = pp[i >> 1] + (i & 1);
-                    scol[i] = ld_stream(a.stage_s + q);
-                    spc[i] = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + q * 4));      // w unused
-                }
-            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t p = pp[r];
@@ -370,19 +372,15 @@ k_band_gather(const BandGatherArgs a)
                         if (inr[i]) dback[(p + j) * 4 + 3] = phz;                 // the tile ray supplies colour and xyz, never w
                         else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
                     }
-                    if (inr[i] && !hole) {                                       // ... from the staging buffers
-                        out[j] = scol[i];
-                        *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc[i].x, spc[i].y);
-                        dback[(p + j) * 4 + 2] = spc[i].z;
-                    }
                 }
                 if (hole) continue;                                              // the hole rays own this cell
-                if (even) {
+                const bool w0 = !inr[2 * r], w1 = !inr[2 * r + 1];               // (the tile rectangle's pixels are the tile rays')
+                if (even && w0 && w1) {
                     *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
                     *reinterpret_cast<uint2 *>(a.tex + p) = make_uint2(colorize_word(out[0]), colorize_word(out[1]));
                 } else {
-                    dscreen[p] = out[0]; a.tex[p] = colorize_word(out[0]);
-                    dscreen[p + 1] = out[1]; a.tex[p + 1] = colorize_word(out[1]);
+                    if (w0) { dscreen[p] = out[0]; a.tex[p] = colorize_word(out[0]); }
+                    if (w1) { dscreen[p + 1] = out[1]; a.tex[p + 1] = colorize_word(out[1]); }
                 }
             }
         }
@@ -407,40 +405,42 @@ k_band_gather(const BandGatherArgs a)
             for (int i = 0; i < 4; ++i) if (rflags & (1u << i)) *o++ = (uint32_t)(pp[i >> 1] + (i & 1));
         }
     }
-    if (m.rank != 0) __threadfence_system();                                // colorized words stored into the writer's frame
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// hole rays of this rank's id list (idsize = its block count); colorized words go straight into the writer's frame
+// hole rays of this rank's id list (idsize = its block count).  Lane stride S as in k_rays_holes, but up to 32: with the
+// image shared by 8 ranks a rank has so few hole rays that every ray gets a warp of its own -- a warp lasts as long as the
+// union of its lanes' paths, and even the four rays of one 2x2 cell cost a third more than one (profiles/r2_ray_latency.md).
 template <int D>
 __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct,
-                  const uint32_t *__restrict__ idb, int idsize, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs, int remote_tex)
+                  const uint32_t *__restrict__ idb, int idsize, uint32_t root, int res_x, int res_y, RayCam cam, FusedScratch fs, int smax)
 {
     __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     const long long total = (long long)idb[0];
     const long long nthreads = (long long)gridDim.x * kRaysBlock;
-    int S = 1;                                         // lane stride: every S-th lane takes a ray while the grid has room (k_rays_holes)
-    while (S < 8 && total * (S * 2) <= nthreads) S *= 2;
+    int S = 1;
+    while (S < smax && total * (S * 2) <= nthreads) S *= 2;
     const long long gtid = (long long)blockIdx.x * kRaysBlock + threadIdx.x;
     if (gtid % S) return;
-    bool wrote = false;
     for (long long w = gtid / S; w < total; w += nthreads / S) {
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
         trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
-        wrote = true;
     }
-    if (wrote && remote_tex) __threadfence_system();
 }
 
 // rays for the owned rows of the rectangle [x0, x0+gx) x [y0, y0+gy) clipped to the screen, 8x4 footprints per warp:
-// the tile refresh (raycast_fine_2, kernel.cl:846-942) and, with the whole screen as the rectangle, a banded full raycast
+// the tile refresh (raycast_fine_2, kernel.cl:846-942) and, with the whole screen as the rectangle, a banded full raycast.
+// `spread` (a power of two <= 8, 1 for a full raycast): only every spread-th lane takes a ray, so a footprint's 32 rays are
+// dealt to `spread` warps (row segments of 8 / spread.. pixels).  The tile refresh of a rank that shares the image with others is
+// a few ten thousand rays -- a latency-bound launch that lasts as long as its slowest warp, i.e. as the union of that warp's
+// divergent paths; fewer rays per warp shorten it (profiles/r2_ray_latency.md) and the idle SMs absorb the extra warps.
 template <int D, bool STRAIGHT>      // STRAIGHT: the sparse tile refresh; false: a full-screen raycast (ray.cuh, fetch_child)
 __global__ void __launch_bounds__(kRaysBlock)
 k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const uint32_t *__restrict__ oct, uint32_t root,
-                 BandMap m, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs)
+                 BandMap m, int gx, int gy, int add_x, int add_y, RayCam cam, FusedScratch fs, int spread)
 {
     __shared__ uint32_t stack[(D + 2) * kRaysBlock];
     // owned rows of the rectangle, enumerated through the local row index so that every launched thread has work
@@ -448,7 +448,9 @@ k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const 
     const int lrows = m.local_rows;
     const int tiles_y = (lrows + 3) / 4;
     const int total = tiles_x * tiles_y * 32;
-    for (int t = blockIdx.x * kRaysBlock + threadIdx.x; t < total; t += gridDim.x * kRaysBlock) {
+    const int gt = blockIdx.x * kRaysBlock + threadIdx.x;
+    if (gt % spread) return;
+    for (int t = gt / spread; t < total; t += gridDim.x * kRaysBlock / spread) {
         const int fp = t >> 5, l = t & 31;
         const int lx = (fp % tiles_x) * 8 + (l & 7), lr = (fp / tiles_x) * 4 + (l >> 3);
         if (lx >= gx || lr >= lrows) continue;
@@ -456,7 +458,30 @@ k_band_rays_rect(uint32_t *__restrict__ screen, float *__restrict__ back, const 
         if (idy < add_y || idy >= add_y + gy || idx >= m.res_x || idy >= m.res_y) continue;
         trace_pixel<D, kRaysBlock, STRAIGHT>(screen, back, oct, root, m.res_x, m.res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
     }
-    if (fs.tex && m.rank != 0) __threadfence_system();                 // colorized words stored into the writer's frame
+    // (banded full raycast: the colorized words go straight into the writer's frame -- peer stores.  No per-thread system fence:
+    // the launch boundary and the release of the barrier kernel that follows order them; a fence here costs 15 % of the launch.)
+}
+
+// The tile rays' staged pixels (owned rows of the rectangle) -> destination slot + the rank's image rows; w stays the
+// reprojection's, as in the reference.  Runs on the tile rays' stream once the destination is free, off the critical path: the
+// gather pass does not wait for the tile rays, it merely leaves the rectangle's colour / xyz alone.  (A hole cell inside the
+// rectangle is also traced by the hole rays: both write the same words.)
+__global__ void __launch_bounds__(256)
+k_band_tile_move(BandMap m, Rect r, const uint32_t *__restrict__ stage_s, const float *__restrict__ stage_b,
+                 uint32_t *__restrict__ dscreen, float *__restrict__ dback, uint32_t *__restrict__ tex)
+{
+    const int w = r.x1 - r.x0, h = r.y1 - r.y0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < w * h; t += gridDim.x * blockDim.x) {
+        const int y = r.y0 + t / w, x = r.x0 + t % w;
+        if (m.owner(y) != m.rank) continue;
+        const size_t p = (size_t)y * m.res_x + x;
+        const uint32_t word = stage_s[p];
+        const float4 pc = *reinterpret_cast<const float4 *>(stage_b + p * 4);          // w unused
+        dscreen[p] = word;
+        tex[p] = colorize_word(word);
+        *reinterpret_cast<float2 *>(dback + p * 4) = make_float2(pc.x, pc.y);
+        dback[p * 4 + 2] = pc.z;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -499,39 +524,48 @@ struct BandSnapView {
     }
 };
 
+__device__ __forceinline__ uint32_t band_fill_pixel(const BandSnapView &view, int p, int res_x)
+{
+    const uint32_t c1 = view[p + 1], c2 = view[p - 1], c3 = view[p + res_x], c4 = view[p - res_x];
+    if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
+        return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
+    if (c1 != kHole && c2 != kHole) return (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
+    if (c3 != kHole && c4 != kHole) return (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+    uint32_t f = c1;                                     // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
+    if (f == kHole) f = c3;
+    if (f == kHole) f = view[p + 1 + res_x];
+    if (f == kHole)                                      // 5x5 search, x offset outer / y offset inner (:461-467)
+        for (int a = -2; a < 3 && f == kHole; ++a)
+            for (int b = -2; b < 3; ++b) {
+                if (f != kHole) break;
+                f = view[p + a + b * res_x];
+            }
+    return f;
+}
+
+// Listed pixels whose 5x5 neighbourhood lies inside the rank's own stripe (all but the 2 + 3 rows at its edges) read the
+// rank's frame directly (fillhole2_view: every load issued before the first test); the edge rows go through the peer view.
 __global__ void __launch_bounds__(256)
 k_band_fill_list(BandMap m, BandPeers P, int dst_slot, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid,
                  const unsigned int *__restrict__ resid_count, PatchList patch)
 {
     const unsigned int cnt = resid_count[0];
     const int n = m.res_x * m.res_y;
-    const BandSnapView view = {&P, m, (size_t)dst_slot * n, n};
     const uint32_t *__restrict__ own = P.screen[m.rank] + (size_t)dst_slot * n;
-    bool wrote = false;
+    const SnapView local = {own, own, n};
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int p = (int)resid[i];
         if (own[p] != kHole) continue;                   // listed before a ray filled it
-        const uint32_t c1 = view[p + 1], c2 = view[p - 1], c3 = view[p + m.res_x], c4 = view[p - m.res_x];
+        const int y = p / m.res_x, j = y % m.SR;
         uint32_t f;
-        if (c1 != kHole && c2 != kHole && c3 != kHole && c4 != kHole)
-            f = (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu) + (c3 & 0xfcu) + (c4 & 0xfcu)) >> 2) & 0xfcu);
-        else if (c1 != kHole && c2 != kHole) f = (c1 & 3u) + ((((c1 & 0xfcu) + (c2 & 0xfcu)) >> 1) & 0xfcu);
-        else if (c3 != kHole && c4 != kHole) f = (c3 & 3u) + ((((c3 & 0xfcu) + (c4 & 0xfcu)) >> 1) & 0xfcu);
+        if (m.G == 1 || (j >= 2 && j < m.SR - 3 && y + 3 < m.res_y)) f = fillhole2_view(local, p, m.res_x);
         else {
-            f = c1;                                      // i = 1 of the 2x2 probe (:453-458); i = 0 is the hole itself
-            if (f == kHole) f = c3;
-            if (f == kHole) f = view[p + 1 + m.res_x];
-            if (f == kHole)                              // 5x5 search, x offset outer / y offset inner (:461-467)
-                for (int a = -2; a < 3 && f == kHole; ++a)
-                    for (int b = -2; b < 3; ++b) {
-                        if (f != kHole) break;
-                        f = view[p + a + b * m.res_x];
-                    }
+            const BandSnapView view = {&P, m, (size_t)dst_slot * n, n};
+            f = band_fill_pixel(view, p, m.res_x);
         }
         patch.value[p] = f;
-        if (f != kHole) { tex[p] = colorize_word(f); wrote = true; }
+        if (f != kHole) tex[p] = colorize_word(f);
     }
-    if (wrote && m.rank != 0) __threadfence_system();
 }
 
 }  // namespace svo
