@@ -23,6 +23,9 @@ enum { SVO_MODE_REFERENCE = 0,   /* the 13 launches of raycast_draw one by one, 
 /* octree_init + raycast_init.  octree: built by svo_octree_build*() (copied to the device; the caller keeps ownership).
  * max_w/max_h = WINDOW_WIDTH_MAX/WINDOW_HEIGHT_MAX (src/main.cpp:49-50; reference 2048x1080).  Returns 0 on success. */
 int  svo_raycast_init(svo_octree_t octree, int max_w, int max_h, int device, int mode);
+/* the same for a compact octree array the caller already holds (octree_array_compact + octree_root_normal, src/raycast.h:38-39,68) */
+int  svo_raycast_init_words(const uint32_t *words, size_t nwords, uint32_t octree_root_normal, int depth,
+                            int max_w, int max_h, int device, int mode);
 void svo_raycast_exit(void);
 /* pos in world units (reference start: 1,50,1 src/raycast.h:113), rot = (rot.x, rot.y, rot.z) radians (:114-117) */
 void svo_raycast_set_camera(const float pos[3], const float rot[3]);
@@ -30,6 +33,8 @@ void svo_raycast_set_camera(const float pos[3], const float rot[3]);
 void svo_raycast_draw(int res_x, int res_y, int sync);
 int  svo_raycast_frame(void);                      /* frame counter of the last draw (first frame = 0) */
 void svo_raycast_reset(void);                      /* frame counter back to -1 (next draw is frame 0: full raycast) */
+void svo_raycast_set_frame(int frame);             /* frame counter of the LAST draw (hosts that also issue frames through svo_frame_fused themselves) */
+void svo_raycast_set_mode(int mode);               /* SVO_MODE_* of the following draws */
 /* SVO_MODE_REFERENCE only: copy target ((frame>>4)%2)+1, the variant the reference keeps in a comment at src/raycast.h:395,
  * instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames.  0 = ok. */
 int  svo_raycast_set_cache_rotation(int on);
@@ -41,7 +46,7 @@ void svo_raycast_read_frame(uint32_t *dst_host, int res_x, int res_y);
 void svo_raycast_read_frame_async(uint32_t *dst_pinned, int res_x, int res_y);
 int  svo_raycast_write_ppm(const char *path, int res_x, int res_y);
 /* the device buffers, for inspection through svo_copy_to_host (names as in src/raycast.h:2-8,268) */
-svo_mem_t svo_raycast_mem(const char *name);       /* "octree" "backbuffer" "screenbuffer" "screenbuffer_tex" "idbuffer" */
+svo_mem_t svo_raycast_mem(const char *name);       /* "octree" "backbuffer" "screenbuffer" "screenbuffer_tex" "idbuffer" "z" */
 
 #ifdef __cplusplus
 }

@@ -50,19 +50,20 @@ void param_f4(const float *v) { svo_param(16, v); }
 
 }  // namespace
 
-extern "C" int svo_raycast_init(svo_octree_t octree, int max_w, int max_h, int device, int mode)
+extern "C" int svo_raycast_init_words(const uint32_t *words, size_t nwords, uint32_t octree_root_normal, int depth,
+                                      int max_w, int max_h, int device, int mode)
 {
-    if (!octree) return -1;
+    if (!words || !nwords) return -1;
     if (int rc = svo_init(device)) return rc;                                   // ocl_init()  src/main.cpp:199
     S = State();
     S.mode = mode;
     if (max_w > 0) S.max_w = max_w;
     if (max_h > 0) S.max_h = max_h;
-    S.octree_depth = svo_octree_depth(octree);
+    S.octree_depth = depth;
     svo_set_octree_depth(S.octree_depth);
-    S.octree_root_normal = svo_octree_root(octree);
+    S.octree_root_normal = octree_root_normal;
     const size_t size = (size_t)S.max_w * S.max_h;                              // :79
-    S.mem_octree = svo_malloc(svo_octree_num_words(octree) * 4, svo_octree_words(octree));   // :68
+    S.mem_octree = svo_malloc(nwords * 4, words);                               // :68
     S.mem_backbuffer = svo_malloc(size * 16 * 4, nullptr);                      // :82
     S.mem_screenbuffer = svo_malloc(size * 4 * 4, nullptr);                     // :85
     S.mem_screenbuffer_tex = svo_malloc(size * 4, nullptr);                     // PBO stand-in :88-89
@@ -82,6 +83,13 @@ extern "C" int svo_raycast_init(svo_octree_t octree, int max_w, int max_h, int d
     return svo_last_error();
 }
 
+extern "C" int svo_raycast_init(svo_octree_t octree, int max_w, int max_h, int device, int mode)
+{
+    if (!octree) return -1;
+    return svo_raycast_init_words(svo_octree_words(octree), svo_octree_num_words(octree), svo_octree_root(octree), svo_octree_depth(octree),
+                                  max_w, max_h, device, mode);
+}
+
 extern "C" void svo_raycast_exit(void)                                          // :511-517
 {
     if (!S.ready) return;
@@ -99,6 +107,8 @@ extern "C" void svo_raycast_set_camera(const float pos[3], const float rot[3])
 
 extern "C" int svo_raycast_frame(void) { return S.frame; }
 extern "C" void svo_raycast_reset(void) { S.frame = -1; }
+extern "C" void svo_raycast_set_frame(int frame) { S.frame = frame; }
+extern "C" void svo_raycast_set_mode(int mode) { S.mode = mode; }
 extern "C" int svo_raycast_set_cache_rotation(int on)
 {
     if (on && S.mode != SVO_MODE_REFERENCE) return -1;      // the fused frame implements the shipped copy target (2)
@@ -233,5 +243,6 @@ extern "C" svo_mem_t svo_raycast_mem(const char *name)
     if (n == "screenbuffer") return S.mem_screenbuffer;
     if (n == "screenbuffer_tex") return S.mem_screenbuffer_tex;
     if (n == "idbuffer") return S.mem_idbuffer;
+    if (n == "z") return S.mem_z;
     return nullptr;
 }

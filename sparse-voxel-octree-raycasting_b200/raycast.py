@@ -1,16 +1,17 @@
-"""Python mirror of the reference's frame driver src/raycast.h on top of ocl.py (-> libsvo_b200.so).
+"""Python face of the frame driver (include/svo_raycast.h, host/raycast_host.cpp -- the C mirror of the reference's
+src/raycast.h) on top of ocl.py (-> libsvo_b200.so).
 
-Same entry points and call sequence as the reference: ``raycast_init()`` (:61-91), ``raycast_draw(res_x, res_y)``
-(:93-510), ``raycast_exit()`` (:511-517).  What the window supplied in the reference (MOUSE_X/Y -> rot,
-WASD -> pos, :113-133) is set explicitly with ``set_camera(pos, rot)``; the GL blit (:449-472) is replaced by
-``read_frame()`` (headless framebuffer).
+Same entry points as the reference: ``raycast_init()`` (:61-91), ``raycast_draw(res_x, res_y)`` (:93-510),
+``raycast_exit()`` (:511-517).  What the window supplied in the reference (MOUSE_X/Y -> rot, WASD -> pos, :113-133) is set
+explicitly with ``set_camera(pos, rot)``; the GL blit (:449-472) is replaced by ``read_frame()`` (headless framebuffer).
 
-``mode="reference"`` issues the reference's 13 launches one by one through ocl_begin/ocl_param/ocl_end with the
-argument lists of the call sites, including the blocking 4-byte readback of idbuf_size (:298).
-``mode="fused"`` issues the same frame through ``svo_frame_fused`` (no host readback); results are identical.
-``mode="pingpong"`` is the fused frame with SVO_FRAME_PINGPONG: no cache copy, frames alternate between buffers 0 and 2
-(``last_slot()`` says where the frame is); the id buffer and the colorized image are identical to the reference's, the
-slot rendered into holds what the reference's cache buffer 2 holds.
+There is ONE restatement of the reference's launch sequence, the C driver: ``raycast_draw`` calls ``svo_raycast_draw``, which
+in ``mode="reference"`` issues the reference's 13 launches one by one through svo_begin / svo_param / svo_end with the
+argument lists of the call sites (including the blocking 4-byte readback of idbuf_size, :298), in ``mode="fused"`` the same
+frame through ``svo_frame_fused`` (no host readback; results identical) and in ``mode="pingpong"`` the fused frame with
+SVO_FRAME_PINGPONG (no cache copy, frames alternate between buffers 0 and 2; ``last_slot()`` says where the frame is).
+This module adds what a Python host needs around it: the buffers as ``ocl.Mem`` objects, camera blocks prepared ahead of
+a frame loop (``prepare_params`` / ``draw_prepared`` / ``draw_present``), and read-backs for parity checks.
 """
 import ctypes as C
 import math
@@ -67,38 +68,57 @@ def wrap_pos(pos, depth=None):
     return (p / f32(16.0)).astype(np.float32)
 
 
+_MODES = {"reference": 0, "fused": 1, "pingpong": 2}          # SVO_MODE_* of include/svo_raycast.h
+_sig = ocl._sig
+_rc_init_words = _sig("svo_raycast_init_words", C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+_rc_exit = _sig("svo_raycast_exit", None)
+_rc_set_camera = _sig("svo_raycast_set_camera", None, C.c_void_p, C.c_void_p)
+_rc_draw = _sig("svo_raycast_draw", None, C.c_int, C.c_int, C.c_int)
+_rc_set_frame = _sig("svo_raycast_set_frame", None, C.c_int)
+_rc_set_mode = _sig("svo_raycast_set_mode", None, C.c_int)
+_rc_set_cache_rotation = _sig("svo_raycast_set_cache_rotation", C.c_int, C.c_int)
+_rc_idbuf_size = _sig("svo_raycast_idbuf_size", C.c_int)
+_rc_last_camera = _sig("svo_raycast_last_camera", None, C.c_void_p)
+_rc_mem = _sig("svo_raycast_mem", C.c_void_p, C.c_char_p)
+
+
 def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth=11, device=0, mode="fused", cache_rotation=False):
-    """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree).
+    """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree): svo_raycast_init_words.
     cache_rotation (launch-by-launch "reference" mode only): copy target `((frame>>4)%2)+1`, the variant the reference keeps
     in a comment at src/raycast.h:395, instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames."""
     if cache_rotation and mode != "reference":
         raise ValueError("cache_rotation needs mode='reference' (the fused frame implements the shipped copy target, 2)")
-    S.cache_rotation = bool(cache_rotation)
     global WINDOW_WIDTH_MAX, WINDOW_HEIGHT_MAX, OCTREE_DEPTH
     if max_w:
         WINDOW_WIDTH_MAX = max_w
     if max_h:
         WINDOW_HEIGHT_MAX = max_h
     OCTREE_DEPTH = depth
-    ocl.ocl_init(device)
-    ocl.set_octree_depth(depth)
     octree_words = np.ascontiguousarray(octree_words, dtype=np.uint32)
+    rc_ = _rc_init_words(octree_words.ctypes.data, len(octree_words), int(octree_root_normal), depth, WINDOW_WIDTH_MAX, WINDOW_HEIGHT_MAX,
+                         device, _MODES[mode])
+    ocl._check()
+    if rc_:
+        raise RuntimeError(f"svo_raycast_init_words failed ({rc_})")
     size = WINDOW_WIDTH_MAX * WINDOW_HEIGHT_MAX
-    S.mem_octree = ocl.ocl_malloc(octree_words.nbytes, octree_words)             # :68
-    S.mem_bvh_nodes = None                                                         # never allocated (:71)
-    S.mem_bvh_childs = None                                                        # never allocated (:74)
-    S.mem_stack = None            # the reference allocates 128 MiB no kernel ever touches (:77); not reproduced
-    S.mem_backbuffer = ocl.ocl_malloc(size * 16 * 4)                               # :82
-    S.mem_screenbuffer = ocl.ocl_malloc(size * 4 * 4)                              # :85
-    S.mem_screenbuffer_tex = ocl.ocl_malloc(size * 4)                              # PBO stand-in (:88-89)
+
+    def mem(name, nbytes):
+        return ocl.Mem(_rc_mem(name.encode()), nbytes)                             # owned by the C driver (raycast_exit frees them)
+
+    S.mem_octree = mem("octree", octree_words.nbytes)                              # :68
+    S.mem_bvh_nodes = S.mem_bvh_childs = S.mem_stack = None                        # never allocated / never touched (:71-77)
+    S.mem_backbuffer = mem("backbuffer", size * 16 * 4)                            # :82
+    S.mem_screenbuffer = mem("screenbuffer", size * 4 * 4)                         # :85
+    S.mem_screenbuffer_tex = mem("screenbuffer_tex", size * 4)                     # PBO stand-in (:88-89)
     S.mem_screenbuffer_tex2 = None                                                 # second colorize target (draw_present)
     S.present_tex = []                                                             # colorize targets of the frames in flight
     S.mem_x = S.mem_y = None                                                       # dead kernel arguments (:170-171)
-    S.mem_z = ocl.ocl_malloc(4 * size)                                             # :172 (only ever memset)
-    # :268-270 allocates MAXPIX + MAXB words, but counts + offsets + ids need N + 2B: the reference overruns by B words
-    # when the window is at its maximum size.  Allocated N + 2B here.
-    S.mem_idbuffer = ocl.ocl_malloc((size + 2 * (WINDOW_WIDTH_MAX // 16) * (WINDOW_HEIGHT_MAX // 16)) * 4)
+    S.mem_z = mem("z", 4 * size)                                                   # :172 (only ever memset)
+    S.mem_idbuffer = mem("idbuffer", (size + 2 * (WINDOW_WIDTH_MAX // 16) * (WINDOW_HEIGHT_MAX // 16)) * 4)
     S.octree_root_normal = int(octree_root_normal)
+    S.cache_rotation = bool(cache_rotation)
+    if cache_rotation and _rc_set_cache_rotation(1):
+        raise RuntimeError("svo_raycast_set_cache_rotation failed")
     S.frame = -1
     S.pos = np.array([1, 50, 1], dtype=np.float32)                                 # :113
     S.rot = np.array([0.0001, 0, 0], dtype=np.float32)                             # :114
@@ -125,101 +145,22 @@ def tile_origin(frame, res_x, res_y):
 
 
 def raycast_draw(res_x, res_y):
-    """One frame; returns the camera actually used (after the wrap of :136-145)."""
+    """One frame through the C driver (svo_raycast_draw, synchronous); returns the camera actually used (after the wrap of
+    :136-145)."""
+    _rc_set_mode(_MODES[S.mode])
+    _rc_set_frame(S.frame)                          # this module's counter is the master (draw_prepared issues frames itself)
+    pos = np.ascontiguousarray(S.pos, dtype=np.float32)
+    rot = np.ascontiguousarray(S.rot, dtype=np.float32)
+    _rc_set_camera(pos.ctypes.data, rot.ctypes.data)
+    _rc_draw(res_x, res_y, 1)
+    ocl._check()
     S.frame += 1
-    frame = S.frame
-    fovx = fovy = f32(1.0)                                                         # :109-110
-    m = rotation_matrix(S.rot)
-    S.pos = wrap_pos(S.pos)
-    pos = S.pos
-    v0 = np.array([pos[0], pos[1], pos[2], 1.0], dtype=np.float32)                 # :159
-    rows = [m[i, :].copy() for i in range(3)]                                      # :160-162
-    cols = [m[:, i].copy() for i in range(3)]                                      # :322-325
-    S.last_camera = dict(pos=pos.copy(), v0=v0, rows=rows, cols=cols)
-    if S.mode in ("fused", "pingpong"):
-        p = ocl.FrameParams()
-        p.res_x, p.res_y, p.frame = res_x, res_y, frame
-        p.v0[:] = v0.tolist()
-        for i in range(3):
-            p.rows[i][:] = rows[i].tolist()
-            p.cols[i][:] = cols[i].tolist()
-        p.fovx, p.fovy = fovx, fovy
-        p.flags = ocl.FRAME_PINGPONG if S.mode == "pingpong" else 0
-        ocl.ocl_begin_all_kernels()
-        ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal,
-                        S.mem_screenbuffer_tex, p)
-        ocl.ocl_end_all_kernels()
-        return S.last_camera
-
-    i32, u32, fl = C.c_int, C.c_uint32, C.c_float
-    n = res_x * res_y
-    size_col, size_xyz = n * 4, n * 16                                             # :106-107
-    ocl.ocl_begin_all_kernels()                                                    # :147
-    if frame < 2:
-        ocl.ocl_memset(S.mem_screenbuffer, 0, HOLE, n * 4 * 4)                     # :150-154
-    ocl.ocl_memset(S.mem_screenbuffer, 0, HOLE, n * 4)                             # :157
-    ocl.ocl_memset(S.mem_z, 0, 0xFFFFFFFF, n * 4)                                  # :173
-    for i in range(2):                                                             # :177-198
-        ocl.ocl_begin(_kernel("raycast_proj"), res_x, res_y, 16, 16)
-        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_x, S.mem_y, S.mem_z):
-            ocl.ocl_param(a)
-        for a in (res_x, res_y, frame, (i + 1) * n):
-            ocl.ocl_param(i32(a))
-        for a in (v0, rows[0], rows[1], rows[2]):
-            ocl.ocl_param(a)
-        ocl.ocl_end()
-    for name in ("raycast_counthole", "raycast_sumids", "raycast_writeids"):       # :272-315
-        if name == "raycast_sumids":
-            ocl.ocl_begin(_kernel(name), 1, 1, 1, 1)
-        else:
-            ocl.ocl_begin(_kernel(name), res_x // 16, res_y // 16, 16, 16)
-        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer):
-            ocl.ocl_param(a)
-        for a in (res_x, res_y, frame):
-            ocl.ocl_param(i32(a))
-        ocl.ocl_end()
-        if name == "raycast_sumids":
-            out = np.zeros(1, dtype=np.int32)
-            ocl.ocl_copy_to_host(out, S.mem_idbuffer, 4)                           # :298 blocking readback
-            S.idbuf_size = int(out[0])
-    dead = (0.0, 0.0, 0.0, 0.0)         # a_cam, a_origin, a_dx, a_dy: unused by every kernel
-    if S.idbuf_size > 0:                                                           # :332-359
-        ocl.ocl_begin(_kernel("raycast_holes"), S.idbuf_size, 1, 256, 1)
-        for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree, S.mem_bvh_nodes, S.mem_bvh_childs, S.mem_stack,
-                  S.mem_idbuffer):
-            ocl.ocl_param(a)
-        ocl.ocl_param(u32(S.octree_root_normal))
-        for a in (res_x, res_y, frame, S.idbuf_size):
-            ocl.ocl_param(i32(a))
-        for a in (dead, dead, dead, dead, v0, cols[0], cols[1], cols[2]):
-            ocl.ocl_param(a)
-        ocl.ocl_param(fl(fovx)); ocl.ocl_param(fl(fovy))
-        ocl.ocl_end()
-    add_x, add_y = tile_origin(frame, res_x, res_y)                                # :361-387
-    ocl.ocl_begin(_kernel("raycast_fine_2"), res_x // 8, res_y // 4, 16, 16)
-    for a in (S.mem_screenbuffer, S.mem_backbuffer, S.mem_octree):
-        ocl.ocl_param(a)
-    ocl.ocl_param(u32(S.octree_root_normal))
-    for a in (res_x, res_y, frame, add_x, add_y):
-        ocl.ocl_param(i32(a))
-    for a in (dead, dead, dead, dead, v0, cols[0], cols[1], cols[2]):
-        ocl.ocl_param(a)
-    ocl.ocl_param(fl(fovx)); ocl.ocl_param(fl(fovy))
-    ocl.ocl_end()
-    target = ((frame >> 4) % 2) + 1 if getattr(S, "cache_rotation", False) else 2  # :395
-    ocl.ocl_memcpy(S.mem_screenbuffer, size_col * target, S.mem_screenbuffer, 0, size_col)   # :396-399
-    ocl.ocl_memcpy(S.mem_backbuffer, size_xyz * target, S.mem_backbuffer, 0, size_xyz)       # :401-404
-    ocl.ocl_begin(_kernel("raycast_fillhole2"), res_x, res_y, 16, 16)              # :414-421
-    for a in (S.mem_screenbuffer, S.mem_backbuffer):
-        ocl.ocl_param(a)
-    for a in (res_x, res_y, frame):
-        ocl.ocl_param(i32(a))
-    ocl.ocl_end()
-    ocl.ocl_begin(_kernel("raycast_colorize"), res_x, res_y, 16, 16)               # :430-436
-    ocl.ocl_param(S.mem_screenbuffer); ocl.ocl_param(S.mem_screenbuffer_tex)
-    ocl.ocl_param(i32(res_x)); ocl.ocl_param(i32(res_y))
-    ocl.ocl_end()
-    ocl.ocl_end_all_kernels()                                                      # :438
+    cam = np.zeros(28, dtype=np.float32)
+    _rc_last_camera(cam.ctypes.data)
+    S.pos = cam[:3].copy()                          # wrapped (:136-145)
+    S.idbuf_size = _rc_idbuf_size() if S.mode == "reference" else 0
+    S.last_camera = dict(pos=cam[:3].copy(), v0=cam[:4].copy(), rows=[cam[4 + 4 * i:8 + 4 * i].copy() for i in range(3)],
+                         cols=[cam[16 + 4 * i:20 + 4 * i].copy() for i in range(3)])
     return S.last_camera
 
 
@@ -364,9 +305,6 @@ def raycast_exit():
         m.free()
     S.present_tex, S.mem_screenbuffer_tex2 = [], None
     for name in ("mem_octree", "mem_backbuffer", "mem_screenbuffer", "mem_screenbuffer_tex", "mem_z", "mem_idbuffer"):
-        m = getattr(S, name, None)
-        if m is not None:
-            m.free()
-            setattr(S, name, None)
-    ocl.ocl_exit()
+        setattr(S, name, None)                      # the C driver owns and frees them
+    _rc_exit()
     S.ready = False
