@@ -105,14 +105,19 @@ typedef struct svo_frame_params {
     float rows[3][4];            /* vx,vy,vz = rows of m    (raycast_proj)            src/raycast.h:160-162 */
     float cols[3][4];            /* vx,vy,vz = columns of m (ray kernels)             src/raycast.h:322-325 */
     float fovx, fovy;            /*                                                   src/raycast.h:109-110 */
-    int   flags;                 /* 0 or SVO_FRAME_PINGPONG */
+    int   flags;                 /* 0, SVO_FRAME_PINGPONG or SVO_FRAME_CACHE_ROTATION */
 } svo_frame_params;
 
 /* SVO_FRAME_PINGPONG: do not copy the frame into cache buffer 2 (src/raycast.h:394-405); instead render alternately into
  * buffer 0 and buffer 2 and reproject from the other one.  The slot rendered into (svo_frame_last_slot()) then holds
  * exactly what the reference's cache buffer 2 holds after the frame, the id buffer and the colorized image are
  * identical, and the small-gap filter's output exists in the colorized image only. */
-enum { SVO_FRAME_PINGPONG = 1 };
+enum { SVO_FRAME_PINGPONG = 1,
+       /* SVO_FRAME_CACHE_ROTATION: the copy target the reference keeps in a comment, `((frame>>4)%2)+1` (src/raycast.h:395),
+        * instead of the hard-wired 2: cache buffers 1 and 2 alternate every 16 frames, so both reprojection launches see real
+        * frames (the triple buffer of SURVEY.md 8(f) rank 4).  Every buffer ends the frame as that variant of the reference
+        * leaves it.  Not combinable with SVO_FRAME_PINGPONG. */
+       SVO_FRAME_CACHE_ROTATION = 2 };
 
 /* One whole frame on buffers laid out as the reference's (4 colour + 4 coordinate buffers at stride
  * res_x*res_y, id buffer, octree, colorize target).  Asynchronous; svo_end_all_kernels() waits.

@@ -35,9 +35,14 @@ int  svo_raycast_frame(void);                      /* frame counter of the last 
 void svo_raycast_reset(void);                      /* frame counter back to -1 (next draw is frame 0: full raycast) */
 void svo_raycast_set_frame(int frame);             /* frame counter of the LAST draw (hosts that also issue frames through svo_frame_fused themselves) */
 void svo_raycast_set_mode(int mode);               /* SVO_MODE_* of the following draws */
-/* SVO_MODE_REFERENCE only: copy target ((frame>>4)%2)+1, the variant the reference keeps in a comment at src/raycast.h:395,
- * instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames.  0 = ok. */
+/* copy target ((frame>>4)%2)+1, the variant the reference keeps in a comment at src/raycast.h:395, instead of the hard-wired
+ * 2 -- cache buffers 1 and 2 then both hold real frames.  SVO_MODE_REFERENCE and SVO_MODE_FUSED
+ * (SVO_FRAME_CACHE_ROTATION); not SVO_MODE_PINGPONG.  0 = ok. */
 int  svo_raycast_set_cache_rotation(int on);
+/* SVO_MODE_REFERENCE only: the quality pass the reference keeps behind if(0) -- raycast_fillhole every 4th frame
+ * (src/raycast.h:205-219), fed by the motion vectors raycast_proj then writes into mem_x / mem_y (the producer the reference
+ * keeps commented out, kernel.cl:587-588).  SURVEY.md 8(f) rank 4.  0 = ok. */
+int  svo_raycast_set_quality_passes(int on);
 int  svo_raycast_idbuf_size(void);                 /* hole-ray count of the last frame (:298) */
 /* the camera block the last draw used: v0[4], rows[3][4], cols[3][4] (28 floats) -- for parity harnesses */
 void svo_raycast_last_camera(float out28[28]);
@@ -45,8 +50,16 @@ void svo_raycast_last_camera(float out28[28]);
 void svo_raycast_read_frame(uint32_t *dst_host, int res_x, int res_y);
 void svo_raycast_read_frame_async(uint32_t *dst_pinned, int res_x, int res_y);
 int  svo_raycast_write_ppm(const char *path, int res_x, int res_y);
+/* the same image as a PNG (8-bit RGB; stored-deflate zlib stream, no compression library needed) -- the display/encode stage
+ * of SURVEY.md 8(f) rank 3 for hosts that want a standard container */
+int  svo_raycast_write_png(const char *path, int res_x, int res_y);
+/* host-only PNG writer behind it: 0x00RRGGBB words, row 0 first; flip != 0 writes the last row first (the reference's quad
+ * shows texture row 0 at the bottom, src/raycast.h:459-467) */
+int  svo_write_png(const char *path, const uint32_t *pixels_0rgb, int w, int h, int flip);
+/* raw video: the frame as R,G,B bytes, top row first, appended to an open FILE* (ffmpeg -f rawvideo -pix_fmt rgb24 -s WxH) */
+int  svo_raycast_append_raw_rgb24(void *file, int res_x, int res_y);
 /* the device buffers, for inspection through svo_copy_to_host (names as in src/raycast.h:2-8,268) */
-svo_mem_t svo_raycast_mem(const char *name);       /* "octree" "backbuffer" "screenbuffer" "screenbuffer_tex" "idbuffer" "z" */
+svo_mem_t svo_raycast_mem(const char *name);       /* "octree" "backbuffer" "screenbuffer" "screenbuffer_tex" "idbuffer" "x" "y" "z" */
 
 #ifdef __cplusplus
 }

@@ -167,14 +167,16 @@ class CpuOracle:
         else:
             self._memcpy(nwords, dst, dstofs_words, src, srcofs_words)
 
-    def raycast_proj(self, screen, back, res_x, res_y, frame, ofs_add, m0, mx, my, mz, racy_threads=1):
+    def raycast_proj(self, screen, back, res_x, res_y, frame, ofs_add, m0, mx, my, mz, racy_threads=1, xbuf=None, ybuf=None):
         """racy_threads > 1: the kernel work-group-parallel with its payload race, as an OpenCL CPU runtime runs it -- for
         timing only; the serial form (default) is the defined outcome the parity checks use."""
+        xb = xbuf.ctypes.data if xbuf is not None else None      # int32 motion-vector buffers (C restatement only: the reference
+        yb = ybuf.ctypes.data if ybuf is not None else None      # keeps their producer commented out, kernel.cl:587-588)
         if racy_threads > 1:
-            self._proj_mt(res_x, res_y, 16, 16, racy_threads, screen, back, None, None, None, res_x, res_y, frame, ofs_add,
+            self._proj_mt(res_x, res_y, 16, 16, racy_threads, screen, back, xb, yb, None, res_x, res_y, frame, ofs_add,
                           _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz))
         else:
-            self._proj(res_x, res_y, 16, 16, screen, back, None, None, None, res_x, res_y, frame, ofs_add,
+            self._proj(res_x, res_y, 16, 16, screen, back, xb, yb, None, res_x, res_y, frame, ofs_add,
                        _vec4(m0), _vec4(mx), _vec4(my), _vec4(mz))
 
     def raycast_counthole(self, screen, idbuf, res_x, res_y, frame=0, threads=1):

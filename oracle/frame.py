@@ -63,7 +63,7 @@ def camera_args(pos, rot, depth=11):
 class OracleFrame:
     """State of the reference's frame loop (4 colour + 4 coordinate buffers, id buffer, frame counter)."""
 
-    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11, cache_rotation=False, timed=False):
+    def __init__(self, orc, octree, root, res_x, res_y, threads=1, depth=11, cache_rotation=False, timed=False, quality_passes=False):
         """cache_rotation: the copy target the reference has in a comment, `((frame>>4)%2)+1` (src/raycast.h:395), instead of
         the hard-wired 2 -- the variant that makes the triple buffer real."""
         self.cache_rotation = cache_rotation
@@ -71,6 +71,12 @@ class OracleFrame:
         # CPU runtime would run the frame -- raycast_proj with its payload race.  The result is then not the defined
         # (serial) outcome; parity checks use timed=False.
         self.timed = timed
+        # quality_passes=True: the depth-discontinuity hole punch the reference keeps behind `if(0)` (raycast_fillhole,
+        # src/raycast.h:205-219, every 4th frame) together with the motion-vector producer it needs, which the reference keeps
+        # commented out in raycast_proj (kernel.cl:587-588) -- SURVEY.md 8(f) rank 4.  C restatement only.
+        self.quality_passes = quality_passes
+        self.xbuf = np.zeros(res_x * res_y, dtype=np.int32) if quality_passes else None   # mem_x / mem_y (:170-171)
+        self.ybuf = np.zeros(res_x * res_y, dtype=np.int32) if quality_passes else None
         self.o, self.octree, self.root = orc, octree, root
         self.res_x, self.res_y, self.threads, self.depth = res_x, res_y, threads, depth
         n = res_x * res_y
@@ -99,7 +105,10 @@ class OracleFrame:
             o.memset(self.screen, 0, HOLE, n * 4, threads=mt)
         o.memset(self.screen, 0, HOLE, n, threads=mt)                   # :157
         for i in range(2):                                              # :177-198
-            o.raycast_proj(self.screen, self.back, rx, ry, frame, (i + 1) * n, v0, *cam["rows"], racy_threads=mt)
+            o.raycast_proj(self.screen, self.back, rx, ry, frame, (i + 1) * n, v0, *cam["rows"], racy_threads=mt,
+                           xbuf=self.xbuf, ybuf=self.ybuf)
+        if self.quality_passes and (frame & 3) == 0:                    # :205-219 (if(0) in the reference)
+            o.raycast_fillhole(self.screen, self.back, self.xbuf, self.ybuf, rx, ry, frame, t)
         if stop_after == "proj":
             return cam
         o.raycast_counthole(self.screen, self.idbuf, rx, ry, frame, t)  # :272-282

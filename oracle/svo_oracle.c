@@ -504,7 +504,7 @@ void orc_memcpy_mt(int gx, uint32_t *dst, uint32_t dstofs, uint32_t *src, uint32
 
 /* kernel/kernel.cl:472-592, serial outcome.  Mixed float/double expressions are kept exactly as
  * C evaluates the reference text: `+0.0`, `-0.0` and `<0.05` promote to double (:549,:552-553). */
-static void proj_impl(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back,
+static void proj_impl(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back, int *xb, int *yb,
                       int res_x, int res_y, int ofs_add,
                       const float *m0, const float *mx, const float *my, const float *mz)
 {
@@ -535,22 +535,25 @@ static void proj_impl(int gx, int gy, int lx, int ly, int threads, uint32_t *scr
         }
         if (__atomic_load_n(&screen[ofs], __ATOMIC_RELAXED) != val) continue;                  /* :579 */
         back[ofs * 4 + 0] = pcx; back[ofs * 4 + 1] = pcy; back[ofs * 4 + 2] = pcz; back[ofs * 4 + 3] = phz;
+        /* the producer the reference keeps commented out (kernel.cl:587-588): motion vector of the winner, for the disabled
+         * quality pass raycast_fillhole; only with both buffers given (the shipped configuration passes buffers nobody reads) */
+        if (xb && yb) { xb[ofs] = scrx - idx; yb[ofs] = scry - idy; }
     NDRANGE_END
 }
 void orc_raycast_proj(int gx, int gy, int lx, int ly, uint32_t *screen, float *back, int *xb, int *yb, int *zb,
                       int res_x, int res_y, int frame, int ofs_add,
                       const float *m0, const float *mx, const float *my, const float *mz)
 {
-    (void)xb; (void)yb; (void)zb; (void)frame;
-    proj_impl(gx, gy, lx, ly, 1, screen, back, res_x, res_y, ofs_add, m0, mx, my, mz);
+    (void)zb; (void)frame;
+    proj_impl(gx, gy, lx, ly, 1, screen, back, xb, yb, res_x, res_y, ofs_add, m0, mx, my, mz);
 }
 /* the kernel as an OpenCL CPU runtime would run it: work-group-parallel, payload race included -- timing only */
 void orc_raycast_proj_mt(int gx, int gy, int lx, int ly, int threads, uint32_t *screen, float *back, int *xb, int *yb, int *zb,
                          int res_x, int res_y, int frame, int ofs_add,
                          const float *m0, const float *mx, const float *my, const float *mz)
 {
-    (void)xb; (void)yb; (void)zb; (void)frame;
-    proj_impl(gx, gy, lx, ly, threads, screen, back, res_x, res_y, ofs_add, m0, mx, my, mz);
+    (void)zb; (void)frame;
+    proj_impl(gx, gy, lx, ly, threads, screen, back, xb, yb, res_x, res_y, ofs_add, m0, mx, my, mz);
 }
 
 /* 2x2 cell of holes?  kernel/kernel.cl:266-271 / :327-332, HOLE_PIXEL_THRESHOLD 4 */

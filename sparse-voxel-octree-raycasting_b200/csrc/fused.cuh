@@ -135,10 +135,13 @@ __device__ __forceinline__ uint32_t fillhole2_view(const SnapView &s, int ofs, i
 #define SVO_SCATTER_PIX 1            // source pixels per thread (loads of all of them in flight before the first use)
 #endif
 constexpr int kScatterPix = SVO_SCATTER_PIX;
+// `mark` != nullptr (rotating cache target, SVO_FRAME_CACHE_ROTATION): these sources survive the frame -- they are not the
+// buffer the end-of-frame copy overwrites -- so the reference's store "source left the view -> hole" (kernel.cl:559-562) is
+// observable in later frames and is issued: into the copy when this pass makes one, else in place (`mark` = the source buffer).
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
                 int res_x, int res_y, unsigned int src0, unsigned int nsrc, unsigned int key_bias, ProjCam c,
-                uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b)
+                uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b, uint32_t *mark = nullptr)
 {
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int q0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,7 +164,10 @@ k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ b
         if (copy_s) { copy_s[q] = word[i]; copy_b[q] = pc[i]; }
         if (word[i] == kHole) continue;
         int sx, sy; float phz;
-        if (!proj_point_fast(c, pc[i].x, pc[i].y, pc[i].z, res_x, res_y, sx, sy, phz)) continue;
+        if (!proj_point_fast(c, pc[i].x, pc[i].y, pc[i].z, res_x, res_y, sx, sy, phz)) {
+            if (mark) { if (copy_s) copy_s[q] = kHole; else mark[q + src0] = kHole; }
+            continue;
+        }
         atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (q + src0 + key_bias));
     }
 }

@@ -521,10 +521,10 @@ static void do_proj_scatter(svo_ctx_t c, uint32_t *screen, float *back, int res_
     ensure_key(c, n);
     { LAUNCH(c, "k_proj_scatter"); k_proj_scatter<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, ofs_add, cam); }
 }
-static void do_proj_resolve(svo_ctx_t c, uint32_t *screen, float *back, int res_x, int res_y, const ProjCam &cam)
+static void do_proj_resolve(svo_ctx_t c, uint32_t *screen, float *back, int res_x, int res_y, const ProjCam &cam, int *xb, int *yb)
 {
     const size_t n = (size_t)res_x * res_y;
-    { LAUNCH(c, "k_proj_resolve"); k_proj_resolve<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, cam); }
+    { LAUNCH(c, "k_proj_resolve"); k_proj_resolve<<<bw_grid(c, n, 256, 16), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, cam, xb, yb); }
 }
 
 static void do_counthole(svo_ctx_t c, const uint32_t *screen, uint32_t *idb, int res_x, int res_y)
@@ -746,7 +746,9 @@ extern "C" void svo_end(void)
         const int res_x = arg<int>(5), res_y = arg<int>(6), ofs_add = arg<int>(8);
         const ProjCam cam = make_proj_cam(arg_f4(9), arg_f4(10), arg_f4(11), arg_f4(12));
         do_proj_scatter(c, screen, back, res_x, res_y, ofs_add, cam);
-        do_proj_resolve(c, screen, back, res_x, res_y, cam);
+        // a_xbuffer / a_ybuffer (arguments 2, 3): NULL in the reference's shipped configuration (dead arguments); when the host
+        // passes buffers the winners' motion vectors are written there (kernel.cl:587-588, commented out in the reference)
+        do_proj_resolve(c, screen, back, res_x, res_y, cam, (int *)arg_u32p(2), (int *)arg_u32p(3));
         break;
     }
     case K_COUNTHOLE:
@@ -877,6 +879,9 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     }
     const bool strips = (res_x % 16) || (res_y % 16);
     const bool pingpong = (p->flags & SVO_FRAME_PINGPONG) != 0;
+    const bool rotate = (p->flags & SVO_FRAME_CACHE_ROTATION) != 0;
+    if (rotate && pingpong) { svo_fail(-62, "svo_frame_fused: SVO_FRAME_CACHE_ROTATION and SVO_FRAME_PINGPONG exclude each other"); return; }
+    const int target = rotate ? ((frame >> 4) % 2) + 1 : 2;                // :395 cache buffer this frame is copied into
     // buffer roles (slots of the reference's 4-buffer arrays)
     int dst_slot = 0, src_first = 1, src_count = 2;                       // exact: project buffers 1 and 2 into buffer 0
     if (pingpong) {
@@ -962,12 +967,26 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
         tile_launched = true;
     }
-    {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
+    if (!rotate) {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = from0 ? n : (unsigned int)src_count * n;
         k_proj_scatter2<<<(nsrc + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
                                                                   nsrc, from0 ? 2u * n : 0u, pc, from0 ? screen + 2 * (size_t)n : nullptr,
                                                                   from0 ? reinterpret_cast<float4 *>(back) + 2 * (size_t)n : nullptr);
+    } else {
+        // Rotating cache target: both cache buffers hold real frames, one launch per source buffer.  The keys carry the source
+        // offset, so "buffer 1 beats buffer 2 on depth ties" (the earlier launch of the reference) falls out of the min whatever
+        // the order here.  A buffer that survives this frame (every one but `target`) gets the reference's source-side store.
+        const unsigned int grid = (n + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix);
+        const unsigned int lazy_slot = from0 ? (unsigned int)((c->pend_dst_s - screen) / n) : 0u;      // where the carried copy lands
+        for (unsigned int slot = 1; slot <= 2; ++slot) {
+            LAUNCH(c, "k_proj_scatter2");
+            const bool carried = from0 && slot == lazy_slot;
+            uint32_t *mark = (int)slot != target ? screen : nullptr;
+            if (carried) k_proj_scatter2<<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, 0u, n, slot * n, pc, screen + (size_t)slot * n,
+                                                                     reinterpret_cast<float4 *>(back) + (size_t)slot * n, mark);
+            else         k_proj_scatter2<<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, slot * n, n, 0u, pc, nullptr, nullptr, mark);
+        }
     }
     if (!split) join_fill();
     if (overlap && !tile_launched) {
@@ -1017,12 +1036,12 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         if (!lazy && !pingpong) {   // SVO_NO_LAZY_COPY: :394-405 cache copy + :429-437 colorize now, on the main stream
             LAUNCH(c, "k_copy_colorize");
             k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
-                dscreen, reinterpret_cast<const float4 *>(dback), screen + 2 * (size_t)n, reinterpret_cast<float4 *>(back) + 2 * (size_t)n, tex, (int)n);
+                dscreen, reinterpret_cast<const float4 *>(dback), screen + (size_t)target * n, reinterpret_cast<float4 *>(back) + (size_t)target * n, tex, (int)n);
         }
         CU_CHECK(cudaEventRecord(c->ev_rays_done, c->stream));
         if (lazy) {
             c->copy_pending = true;
-            c->pend_src_s = dscreen; c->pend_src_b = dback; c->pend_dst_s = screen + 2 * (size_t)n; c->pend_dst_b = back + 2 * (size_t)n * 4;
+            c->pend_src_s = dscreen; c->pend_src_b = dback; c->pend_dst_s = screen + (size_t)target * n; c->pend_dst_b = back + (size_t)target * n * 4;
             c->pend_n = n; c->pend_res_x = res_x;
         }
         // :411-422 gap filter: reads the pre-filter frame (the destination slot: nothing writes it before the next frame's

@@ -104,8 +104,11 @@ __global__ void k_proj_scatter(uint32_t *__restrict__ screen, const float *__res
     }
 }
 
+// xbuf / ybuf != nullptr: the motion-vector producer the reference keeps commented out at kernel.cl:587-588 -- the winner
+// stores (destination - source) pixel coordinates for the disabled quality pass raycast_fillhole (:342-401) to read.
 __global__ void k_proj_resolve(uint32_t *__restrict__ screen, float *__restrict__ back,
-                               unsigned long long *__restrict__ key, int res_x, int res_y, ProjCam c)
+                               unsigned long long *__restrict__ key, int res_x, int res_y, ProjCam c,
+                               int *__restrict__ xbuf = nullptr, int *__restrict__ ybuf = nullptr)
 {
     const int n = res_x * res_y;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -120,6 +123,11 @@ __global__ void k_proj_resolve(uint32_t *__restrict__ screen, float *__restrict_
         proj_point(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz);
         screen[p] = sz + (col & 255u);
         *reinterpret_cast<float4 *>(back + (size_t)p * 4) = make_float4(pc.x, pc.y, pc.z, phz);   // :582-585
+        if (xbuf && ybuf) {                                                  // :587-588 a_xbuffer[ofs] = scr.x - idx, a_ybuffer[ofs] = scr.y - idy
+            const int src = (int)(srcofs % (uint32_t)n);
+            xbuf[p] = p % res_x - src % res_x;
+            ybuf[p] = p / res_x - src / res_x;
+        }
     }
 }
 

@@ -28,6 +28,7 @@ class FrameParams(C.Structure):
 
 
 FRAME_PINGPONG = 1
+FRAME_CACHE_ROTATION = 2
 
 
 def _sig(name, res, *args):

@@ -77,6 +77,7 @@ _rc_draw = _sig("svo_raycast_draw", None, C.c_int, C.c_int, C.c_int)
 _rc_set_frame = _sig("svo_raycast_set_frame", None, C.c_int)
 _rc_set_mode = _sig("svo_raycast_set_mode", None, C.c_int)
 _rc_set_cache_rotation = _sig("svo_raycast_set_cache_rotation", C.c_int, C.c_int)
+_rc_set_quality_passes = _sig("svo_raycast_set_quality_passes", C.c_int, C.c_int)
 _rc_idbuf_size = _sig("svo_raycast_idbuf_size", C.c_int)
 _rc_last_camera = _sig("svo_raycast_last_camera", None, C.c_void_p)
 _rc_mem = _sig("svo_raycast_mem", C.c_void_p, C.c_char_p)
@@ -84,10 +85,10 @@ _rc_mem = _sig("svo_raycast_mem", C.c_void_p, C.c_char_p)
 
 def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth=11, device=0, mode="fused", cache_rotation=False):
     """src/raycast.h:61-91 (octree_init is replaced by the caller handing in the compact octree): svo_raycast_init_words.
-    cache_rotation (launch-by-launch "reference" mode only): copy target `((frame>>4)%2)+1`, the variant the reference keeps
-    in a comment at src/raycast.h:395, instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames."""
-    if cache_rotation and mode != "reference":
-        raise ValueError("cache_rotation needs mode='reference' (the fused frame implements the shipped copy target, 2)")
+    cache_rotation ("reference" and "fused" modes): copy target `((frame>>4)%2)+1`, the variant the reference keeps in a
+    comment at src/raycast.h:395, instead of the hard-wired 2 -- cache buffers 1 and 2 then both hold real frames."""
+    if cache_rotation and mode == "pingpong":
+        raise ValueError("cache_rotation: ping-pong mode has no cache copy to rotate")
     global WINDOW_WIDTH_MAX, WINDOW_HEIGHT_MAX, OCTREE_DEPTH
     if max_w:
         WINDOW_WIDTH_MAX = max_w
@@ -126,6 +127,16 @@ def raycast_init(octree_words, octree_root_normal, max_w=None, max_h=None, depth
     S.idbuf_size = 0
     S.k = {}
     S.ready = True
+
+
+def set_quality_passes(on=True):
+    """mode="reference": enable raycast_fillhole every 4th frame (src/raycast.h:205-219, if(0) in the reference) together with
+    the motion-vector producer in raycast_proj it needs (kernel.cl:587-588, commented out there)."""
+    if _rc_set_quality_passes(1 if on else 0):
+        raise ValueError("quality passes need mode='reference'")
+    size = WINDOW_WIDTH_MAX * WINDOW_HEIGHT_MAX
+    S.mem_x = ocl.Mem(_rc_mem(b"x"), 4 * size) if on else None
+    S.mem_y = ocl.Mem(_rc_mem(b"y"), 4 * size) if on else None
 
 
 def _kernel(name):
@@ -175,7 +186,7 @@ def prepare_params(res_x, res_y, frame):
         p.rows[i][:] = m[i, :].tolist()
         p.cols[i][:] = m[:, i].tolist()
     p.fovx = p.fovy = 1.0
-    p.flags = ocl.FRAME_PINGPONG if S.mode == "pingpong" else 0
+    p.flags = ocl.FRAME_PINGPONG if S.mode == "pingpong" else ocl.FRAME_CACHE_ROTATION if getattr(S, "cache_rotation", False) else 0
     return p
 
 

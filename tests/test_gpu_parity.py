@@ -373,23 +373,34 @@ def test_schedule_switches(svo, mode):
         assert got == ref, f"{extra} changes the result"
 
 
-def test_cache_rotation_reference_mode(svo, orc, world):
+@pytest.mark.parametrize("mode,observe", [("reference", True), ("fused", True), ("fused", False)], ids=["reference", "fused", "fused-back-to-back"])
+def test_cache_rotation(svo, orc, world, mode, observe):
     """The copy target the reference keeps in a comment (`((frame>>4)%2)+1`, src/raycast.h:395): cache
-    buffers 1 and 2 alternate every 16 frames, so both reprojection launches see real frames and depth ties between them
-    occur (buffer 1 wins: the earlier launch).  Launch-by-launch mode against the oracle, 40 frames, every buffer."""
+    buffers 1 and 2 alternate every 16 frames, so both reprojection launches see real frames, depth ties between them occur
+    (buffer 1 wins: the earlier launch) and the source-side store of raycast_proj (a cached pixel that leaves the view
+    becomes a hole, kernel.cl:559-562) is visible in later frames.  Launch-by-launch and fused (SVO_FRAME_CACHE_ROTATION)
+    against the oracle over 40 frames (two target switches), every buffer; the fused frame also back to back, where the
+    next frame's reprojection carries the copy into the rotating target."""
     octree, root = world
     rx, ry = 320, 192
     n = rx * ry
     O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4, cache_rotation=True)
     rc = svo.raycast
     svo.ocl_exit()
-    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="reference", cache_rotation=True)
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode=mode, cache_rotation=True)
     try:
+        d0 = svo.ocl.frame_deferred_count()
         for f in range(40):
             pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
             O.draw(pos, rot)
             rc.set_camera(pos, rot)
-            rc.raycast_draw(rx, ry)
+            if observe:
+                rc.raycast_draw(rx, ry)
+            else:
+                rc.draw_prepared(rc.prepare_params(rx, ry, f), sync=False)
+                if f != 39:
+                    continue
+                assert svo.ocl.frame_deferred_count() - d0 == 38            # every frame from 2 on carried its predecessor's copy
             screen, back, idb = rc.read_buffers(rx, ry)
             assert rc.idbuf_size() == O.idbuf_size, f"frame {f}"
             assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"frame {f} ids"
@@ -399,7 +410,42 @@ def test_cache_rotation_reference_mode(svo, orc, world):
         assert np.any(O.screen[n:2 * n] != HOLE) and np.any(O.screen[2 * n:3 * n] != HOLE)      # both caches are live
         with pytest.raises(ValueError):
             rc.raycast_exit()
-            rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused", cache_rotation=True)
+            rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="pingpong", cache_rotation=True)
+    finally:
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
+def test_quality_passes_reference_mode(svo, orc, world):
+    """the depth-discontinuity hole punch the reference keeps behind if(0) (raycast_fillhole every 4th frame,
+    src/raycast.h:205-219) made usable: raycast_proj writes the winners' motion vectors into mem_x / mem_y (the producer the
+    reference keeps commented out, kernel.cl:587-588) and the pass runs at its call site.  Launch-by-launch mode against the
+    C restatement with the same two lines enabled: every buffer and both motion-vector buffers over 24 frames."""
+    octree, root = world
+    rx, ry = 320, 192
+    n = rx * ry
+    O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4, quality_passes=True)
+    rc = svo.raycast
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="reference")
+    try:
+        rc.set_quality_passes(True)
+        punched = 0
+        for f in range(24):
+            pos, rot = (10 + 0.4 * f, 22 + 0.05 * f, 9 + 0.3 * f), (0.4 + 0.002 * f, 0.7 + 0.015 * f, 0.0)
+            before = None
+            O.draw(pos, rot)
+            rc.set_camera(pos, rot)
+            rc.raycast_draw(rx, ry)
+            screen, back, idb = rc.read_buffers(rx, ry)
+            assert rc.idbuf_size() == O.idbuf_size, f"frame {f}"
+            assert np.array_equal(rc.S.mem_x.to_numpy(np.int32, n), O.xbuf), f"frame {f} mem_x"
+            assert np.array_equal(rc.S.mem_y.to_numpy(np.int32, n), O.ybuf), f"frame {f} mem_y"
+            assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"frame {f} ids"
+            assert np.array_equal(screen, O.screen[:4 * n]), f"frame {f} colour"
+            assert np.array_equal(back.view(np.uint32), O.back[:16 * n].view(np.uint32)), f"frame {f} xyz"
+            assert np.array_equal(rc.read_frame(rx, ry).ravel(), O.tex), f"frame {f} tex"
+        assert np.any(O.xbuf != 0) and np.any(O.ybuf != 0), "no motion vectors were produced"
     finally:
         rc.raycast_exit()
         svo.ocl_init(0)

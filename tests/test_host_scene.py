@@ -129,3 +129,35 @@ def test_rle4_mip_volumes(svo, orc, tmp_path):
 def test_missing_rle4_is_an_error(svo, tmp_path):
     with pytest.raises(RuntimeError):
         svo.scene.rle4_load(str(tmp_path / "nope.rle4"))
+
+
+def test_png_writer_round_trips(tmp_path):
+    """svo_write_png (display/encode stage): a standards-conforming 8-bit RGB PNG without a compression
+    library -- decoded here with zlib + the PNG chunk rules and compared pixel for pixel, flipped and not."""
+    import ctypes as C
+    import struct
+    import zlib
+    from __graft_entry__ import load_package
+    lib = load_package().ocl.lib
+    lib.svo_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(3)
+    for (w, h), flip in (((37, 11), 0), ((320, 192), 1), ((1920, 1024), 1)):        # the last one spans many 64 KiB stored blocks
+        px = rng.integers(0, 1 << 24, size=(h, w), dtype=np.uint32)
+        path = str(tmp_path / f"t_{w}x{h}.png")
+        assert lib.svo_write_png(path.encode(), px.ctypes.data, w, h, flip) == 0
+        blob = open(path, "rb").read()
+        assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(blob):
+            n, typ = struct.unpack(">I4s", blob[pos:pos + 8])
+            data = blob[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + data) & 0xffffffff, typ
+            chunks.append((typ, data))
+            pos += 12 + n
+        assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+        raw = np.frombuffer(zlib.decompress(chunks[1][1]), dtype=np.uint8).reshape(h, 1 + 3 * w)
+        assert not raw[:, 0].any()                                                       # filter type 0 on every scanline
+        rgb = raw[:, 1:].reshape(h, w, 3).astype(np.uint32)
+        got = (rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2]
+        assert np.array_equal(got, px[::-1] if flip else px)
