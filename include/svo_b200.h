@@ -49,6 +49,11 @@ void svo_set_octree_depth(int depth);
 int  svo_get_octree_depth(void);
 
 /* ---- memory ---------------------------------------------------------------------------------- */
+/* The compact octree handed to the ray kernels (mem_octree, src/raycast.h:68) must have the layout convert_tree_blocks builds
+ * (src/octree/octree.h:232-293; svo_octree_build* produce it word for word): "normal" 10-word nodes down to tree depth D-7 and one
+ * block per depth D-6 node, i.e. BLOCK ROOTS SIT EXACTLY AT KERNEL LEVEL rekursion == 6 (octree.h:245).  The traversal uses
+ * that level for the reference's "parent is a normal node" test (kernel.cl:45); a pool with block roots elsewhere is not
+ * this format and decodes wrong. */
 svo_mem_t svo_malloc(size_t size, const void *host_ptr);                 /* ocl_malloc()       src/ocl.h:200-213 (size 0 -> NULL) */
 void      svo_free(svo_mem_t mem);                                       /* clReleaseMemObject src/raycast.h:514 */
 void      svo_copy_to_host(void *dst, svo_mem_t src, size_t size, size_t srcofs); /* ocl_copy_to_host() src/ocl.h:215-221, blocking */
@@ -71,6 +76,11 @@ void svo_begin_all_kernels(void);                                        /* ocl_
 void svo_end_all_kernels(void);                                          /* ocl_end_all_kernels()   src/ocl.h:253-265 (waits) */
 size_t svo_round_up(int group_size, int global_size);                    /* ocl_round_up() src/ocl.h:188-198 */
 uint64_t svo_launch_count(void);                                         /* CUDA kernels launched by this library so far */
+/* Development aid: schedule A/B switches of the fused frame ("no_overlap", "no_lazy_copy", "no_split_resolve", "no_tile_staging",
+ * "frame_l2_pin", "no_l2_pin", "main_lo" (before svo_init), "holes_smax").  They move work between streams and launches and
+ * never change a result.  The library never reads the environment; a build with -DSVO_NO_DEBUG_SWITCHES compiles the switches
+ * to constants and this call returns -1.  0 = ok, -1 = unknown switch. */
+int      svo_debug_set(const char *name, int value);
 
 /* ---- timing (extension; the reference's profiler is dead code, src/raycast.h:164-166,476-492) ------- */
 /* CUDA events on the context's stream. slot 0..15. elapsed waits for event b. */

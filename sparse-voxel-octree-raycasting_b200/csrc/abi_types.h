@@ -16,5 +16,6 @@ struct svo_mem_s {
     void *dptr;
     size_t bytes;
     int device;
+    svo_ctx_t ctx = nullptr;        // the context the buffer was allocated in (svo_free drains that one, not the current one)
 };
 

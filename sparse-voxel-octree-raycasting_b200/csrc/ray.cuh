@@ -92,6 +92,11 @@ __device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct
 // exactly the reference's.)
 __device__ __forceinline__ uint32_t mask_bytes_popc(const uint32_t *__restrict__ rec, uint32_t n)
 {
+    // A byte-packed record has at most 8 mask bytes, so n <= 8 whenever the value is used (a hit).  The only way to get here
+    // with a larger n is a ray that leaves the loop WITHOUT a hit while inside a block at level 2 (distance > VIEW_DIST_MAX,
+    // unreachable inside a world of 2^(D+1) units): there the reference walks `n` = an in-block word offset bytes of the pool,
+    // possibly past its end.  Clamped: no out-of-range read; the colour of such a miss would be a don't-care word anyway.
+    n = n < 9u ? n : 9u;
     uint32_t sum = 0, w = 0;
     if (n > 1) w = ldg(rec);
     for (uint32_t i = 1; i < n; ++i) {

@@ -32,6 +32,40 @@ extern "C" void svo_clear_error(void) { g_last_error = 0; g_last_error_str[0] = 
 
 static svo_ctx_t g_ctx = nullptr;           // current context (the reference's globals, src/ocl.h:8-16)
 
+// Schedule A/B switches of the fused frame.  They move work between streams and launches, never change
+// a result (tests/test_gpu_parity.py::test_schedule_switches); the product never sets them and never reads the environment.
+// svo_debug_set() is the only way in; a build with -DSVO_NO_DEBUG_SWITCHES compiles them to constants.
+struct SvoDebug {
+    bool no_overlap = false, no_lazy_copy = false, no_split_resolve = false, no_tile_staging = false;
+    bool frame_l2_pin = false, no_l2_pin = false, main_lo = false, band_no_tex = false;
+    int holes_smax = 8;
+};
+#ifdef SVO_NO_DEBUG_SWITCHES
+static const SvoDebug g_dbg;
+extern "C" int svo_debug_set(const char *, int) { return -1; }
+#else
+static SvoDebug g_dbg;
+extern "C" int svo_debug_set(const char *name, int value)
+{
+    if (!name) return -1;
+    const std::string n = name;
+    if (n == "no_overlap") g_dbg.no_overlap = value != 0;
+    else if (n == "no_lazy_copy") g_dbg.no_lazy_copy = value != 0;
+    else if (n == "no_split_resolve") g_dbg.no_split_resolve = value != 0;
+    else if (n == "no_tile_staging") g_dbg.no_tile_staging = value != 0;
+    else if (n == "frame_l2_pin") g_dbg.frame_l2_pin = value != 0;
+    else if (n == "no_l2_pin") g_dbg.no_l2_pin = value != 0;
+    else if (n == "main_lo") g_dbg.main_lo = value != 0;            // before svo_init / svo_ctx_create
+    else if (n == "band_no_tex") g_dbg.band_no_tex = value != 0;
+    else if (n == "holes_smax") g_dbg.holes_smax = value > 0 ? value : 8;
+    else return -1;
+    return 0;
+}
+#endif
+
+static std::vector<svo_ctx_t> g_live_ctx;    // contexts not yet destroyed (svo_free looks its buffer's owner up here)
+static bool svo_ctx_alive(svo_ctx_t c) { for (svo_ctx_t x : g_live_ctx) if (x == c) return true; return false; }
+
 static svo_ctx_t need_ctx()
 {
     if (!g_ctx) svo_fail(-100, "no context: call svo_init() first");
@@ -95,8 +129,8 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     c->num_sms = prop.multiProcessorCount;
     int prio_lo = 0, prio_hi = 0;
     CU_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    // the main stream carries the frame's critical chain: its CTAs go first (SVO_MAIN_LO=1: below the side streams, -1.7 %)
-    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, getenv("SVO_MAIN_LO") ? prio_lo : prio_hi));
+    // the main stream carries the frame's critical chain: its CTAs go first (debug switch main_lo: below the side streams, -1.7 %)
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, g_dbg.main_lo ? prio_lo : prio_hi));
     CU_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_tile_done, cudaEventDisableTiming));
@@ -110,6 +144,7 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_rays_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    g_live_ctx.push_back(c);
     return c;
 }
 
@@ -145,6 +180,7 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     for (auto &e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     if (g_ctx == c) g_ctx = nullptr;
+    for (size_t i = 0; i < g_live_ctx.size(); ++i) if (g_live_ctx[i] == c) { g_live_ctx.erase(g_live_ctx.begin() + i); break; }
     delete c;
 }
 
@@ -184,7 +220,7 @@ extern "C" svo_mem_t svo_malloc(size_t size, const void *host_ptr)
 {
     svo_ctx_t c = need_ctx();
     if (!c || size == 0) return nullptr;                             // src/ocl.h:203
-    svo_mem_t m = new svo_mem_s{nullptr, size, c->device};
+    svo_mem_t m = new svo_mem_s{nullptr, size, c->device, c};
     // 256 B of slack: the reference's fetch loops may read a few words past the last octree record
     CU_CHECK(cudaMalloc(&m->dptr, size + 256));
     if (!m->dptr) { delete m; return nullptr; }
@@ -197,14 +233,17 @@ extern "C" svo_mem_t svo_malloc(size_t size, const void *host_ptr)
 extern "C" void svo_free(svo_mem_t m)
 {
     if (!m) return;
-    if (g_ctx) {
-        // nothing pending may outlive the buffer: the lazy cache copy / gap-filter write of the last fused frame are issued,
-        // then every stream of the context drains
-        flush_patches(g_ctx);
-        for (cudaStream_t st : {g_ctx->stream, g_ctx->stream2, g_ctx->stream3, g_ctx->stream4}) cudaStreamSynchronize(st);
-        if (g_ctx->copy_stream) cudaStreamSynchronize(g_ctx->copy_stream);
+    // nothing pending may outlive the buffer: the lazy cache copy / gap-filter write of the last fused frame of the context that
+    // OWNS the buffer (not necessarily the current one) are issued, then every stream of that context drains
+    svo_ctx_t owner = m->ctx && svo_ctx_alive(m->ctx) ? m->ctx : nullptr;
+    if (owner) {
+        cudaSetDevice(owner->device);
+        flush_patches(owner);
+        for (cudaStream_t st : {owner->stream, owner->stream2, owner->stream3, owner->stream4}) cudaStreamSynchronize(st);
+        if (owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
     }
     cudaFree(m->dptr);
+    if (owner && g_ctx && g_ctx != owner) cudaSetDevice(g_ctx->device);
     delete m;
 }
 
@@ -492,7 +531,7 @@ static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes);
 void svo_pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes) { pin_octree_in_l2(c, oct, bytes); }
 static void pin_octree_in_l2(svo_ctx_t c, const void *oct, size_t bytes)
 {
-    if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || getenv("SVO_NO_L2_PIN")) return;
+    if (c->l2_pinned == oct || !c->l2_persist_max || !c->l2_window_max || g_dbg.no_l2_pin) return;
     const size_t win = bytes < c->l2_window_max ? bytes : c->l2_window_max;
     const size_t carve = win < c->l2_persist_max ? win : c->l2_persist_max;
     CU_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
@@ -848,8 +887,9 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     if (!c) return;
     if (!screenbuffer || !backbuffer || !idbuffer || !octree || !p) { svo_fail(-38, "svo_frame_fused: null argument"); return; }
     const int res_x = p->res_x, res_y = p->res_y, frame = p->frame;
+    if (res_x <= 0 || res_y <= 0) { svo_fail(-61, "svo_frame_fused: bad resolution %dx%d", res_x, res_y); return; }
     const uint32_t n = (uint32_t)res_x * (uint32_t)res_y;
-    const int nb = (res_x / 16) * (res_y / 16);
+    const int nb = (res_x / 16) * (res_y / 16);          // 0 when a side is below 16: no hole blocks, no hole rays (kernel.cl:243-244)
     if ((size_t)n * 16 > screenbuffer->bytes || (size_t)n * 64 > backbuffer->bytes || ((size_t)n + 2 * nb) * 4 > idbuffer->bytes) {
         svo_fail(-61, "svo_frame_fused: buffers too small for %dx%d", res_x, res_y);
         return;
@@ -861,9 +901,8 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     // No persisting-L2 window for the octree here: the frame's own buffers (two 20 B/pixel frames, keys, image: ~100 MB at
     // 1920x1024) want the whole 126 MB L2 -- with 31 MB set aside for the node pool the streaming passes write dirty lines
     // back to DRAM that would otherwise have stayed put (6 475 -> 6 690 frames/s without the set-aside; the sparse rays
-    // lose 3 us).  SVO_FRAME_L2_PIN=1 restores it; the band kernels at 3840x2160 (buffers beyond any L2) keep it.
-    static const bool frame_pin = getenv("SVO_FRAME_L2_PIN") != nullptr;
-    if (frame_pin) pin_octree_in_l2(c, oct, octree->bytes);
+    // lose 3 us).  svo_debug_set("frame_l2_pin", 1) restores it; the band kernels at 3840x2160 (buffers beyond any L2) keep it.
+    if (g_dbg.frame_l2_pin) pin_octree_in_l2(c, oct, octree->bytes);
 
     const size_t ncta = ((size_t)nb + kGatherBlocksPerCta - 1) / kGatherBlocksPerCta;
     ensure_key(c, n);
@@ -895,8 +934,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const int add_x = (res_x / 8) * (frame & 7), add_y = (res_y / 4) * ((frame >> 3) & 3);   // :363-364
     const int gx = (int)svo_round_up(16, res_x / 8), gy = (int)svo_round_up(16, res_y / 4);
     const Rect tile = {add_x, add_y, add_x + gx < res_x ? add_x + gx : res_x, add_y + gy < res_y ? add_y + gy : res_y};
-    static const bool overlap = !getenv("SVO_NO_OVERLAP");
-    static const bool lazy_copy = !getenv("SVO_NO_LAZY_COPY");
+    const bool overlap = !g_dbg.no_overlap, lazy_copy = !g_dbg.no_lazy_copy;
     c->epoch = (c->epoch + 1) & 0x3fffffffu;
     if (c->epoch == 0) c->epoch = 4;                                       // keeps the mod-4 counter rotation in step
     FusedScratch fs = c->fs;                                               // this frame's view of the scratch
@@ -926,8 +964,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     // proper runs beside them on the fourth stream and never writes the cells the rays fill.  The tile rays then
     // write into staging buffers (they depend on nothing but the camera, so they start with the frame, beside the
     // reprojection, instead of beside the hole rays) and the gather pass moves their pixels into the destination.
-    static const bool split_resolve = !getenv("SVO_NO_SPLIT_RESOLVE");
-    static const bool stage_tile = !getenv("SVO_NO_TILE_STAGING");
+    const bool split_resolve = !g_dbg.no_split_resolve, stage_tile = !g_dbg.no_tile_staging;
     const bool split = split_resolve && overlap;
     const bool staged = split && stage_tile;
     if (staged && c->stage_pixels < n) {
@@ -1001,10 +1038,10 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const GatherArgs ga = {screen, back, c->key, idb, fs, c->epoch, res_x, res_y, (unsigned int)dst_slot * n, tile, overlap ? 1 : 0, pc, next_resid_count,
                            staged ? c->stage_s : nullptr, staged ? c->stage_b : nullptr};
     if (split) {
-        {   // :272-315 hole gather from the keys alone, ids in the reference's order, idb[0] = idbuf_size
+        if (nb) {   // :272-315 hole gather from the keys alone, ids in the reference's order, idb[0] = idbuf_size
             LAUNCH(c, "k_hole_ids");
             k_hole_ids<<<(unsigned)((nb + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta), 256, 0, c->stream>>>(c->key, idb, fs, c->epoch, res_x, res_y);
-        }
+        } else CU_CHECK(cudaMemsetAsync(idb, 0, 4, c->stream));              // no whole 16x16 block: idbuf_size = 0
         CU_CHECK(cudaEventRecord(c->ev_ids_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_ids_done, 0));                             // (re-arms the keys the id pass reads)
         if (c->fill_outstanding) CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_fill_done, 0));   // (the filter reads buffer 0)
@@ -1016,13 +1053,14 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         CU_CHECK(cudaEventRecord(c->ev_gather_done, c->stream4));
         join_fill();                                                                              // the hole rays write buffer 0 too
     } else {   // :157 clear + depth-test resolve + :272-315 hole gather in one launch
+        if (!nb) CU_CHECK(cudaMemsetAsync(idb, 0, 4, c->stream));               // no whole 16x16 block: idbuf_size = 0
         LAUNCH(c, "k_resolve_gather");
         k_resolve_gather<true><<<(unsigned)(ncta + (strips ? 32 : 0)), 256, 0, c->stream>>>(ga);
     }
     {   // :332-359 hole rays, count on the device
         LAUNCH(c, "k_rays_holes");
         const int grid = c->num_sms * 32;
-        static const int smax = getenv("SVO_HOLES_SMAX") ? atoi(getenv("SVO_HOLES_SMAX")) : 8;
+        const int smax = g_dbg.holes_smax;
         if (c->depth == 11) k_rays_holes<11><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
         else                k_rays_holes<14><<<grid, kRaysBlock, 0, c->stream>>>(dscreen, dback, oct, idb, octree_root, res_x, res_y, rc, fs, smax);
     }
@@ -1033,7 +1071,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         // exact mode, lazy: the copy stays pending (see above).  The gap filter goes to the third stream, behind this
         // frame's rays; it reads the frame itself (buffer 0 == what buffer 2 will hold; the filter's in-place write is not
         // issued inside the pipeline), so the colorized image is complete a few microseconds after the last ray.
-        if (!lazy && !pingpong) {   // SVO_NO_LAZY_COPY: :394-405 cache copy + :429-437 colorize now, on the main stream
+        if (!lazy && !pingpong) {   // debug switch no_lazy_copy: :394-405 cache copy + :429-437 colorize now, on the main stream
             LAUNCH(c, "k_copy_colorize");
             k_copy_colorize<<<bw_grid(c, (size_t)n / 4 + 256, 256, 8), 256, 0, c->stream>>>(
                 dscreen, reinterpret_cast<const float4 *>(dback), screen + (size_t)target * n, reinterpret_cast<float4 *>(back) + (size_t)target * n, tex, (int)n);

@@ -239,7 +239,10 @@ __global__ void k_gather_u32(const uint32_t *__restrict__ src, const uint32_t *_
 static svo_mem_t build_from_device(cudaStream_t st, size_t n, uint32_t *dx, uint32_t *dy, uint32_t *dz, uint32_t *drgba, int depth,
                                    uint32_t *root_out, uint64_t *num_unique_out)
 {
-    const int grid = 148 * 8;
+    int dev = 0, sms = 0;
+    CU_CHECK(cudaGetDevice(&dev));
+    CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 8;                                                     // grid-stride kernels: 8 CTAs per SM
     unsigned long long *key = dalloc<unsigned long long>(n), *key2 = dalloc<unsigned long long>(n);
     uint32_t *idx = dalloc<uint32_t>(n), *idx2 = dalloc<uint32_t>(n);
     k_make_keys<<<grid, 256, 0, st>>>(dx, dy, dz, key, idx, n, (1u << depth) - 1u);

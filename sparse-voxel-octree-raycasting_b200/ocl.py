@@ -242,6 +242,15 @@ def ocl_memset(dst, dstofs, val, size):
     _check()
 
 
+_svo_debug_set = _sig("svo_debug_set", _i, C.c_char_p, _i)
+
+
+def debug_set(name, value=1):
+    """svo_debug_set: schedule A/B switches of the fused frame (development aid; results never change)."""
+    if _svo_debug_set(name.encode(), int(value)):
+        raise ValueError(f"unknown debug switch {name!r}")
+
+
 def ocl_round_up(group_size, global_size):
     return int(_svo_round_up(group_size, global_size))
 

@@ -1,6 +1,6 @@
-"""Worker of test_schedule_switches: renders a short back-to-back fused sequence with whatever SVO_* schedule switches the
-environment carries and prints a digest of every buffer, of the id list and of the last two images (the switches are read
-once per process, so each combination needs a process of its own)."""
+"""Worker of test_schedule_switches: renders a short back-to-back fused sequence with the schedule switches named in
+SVO_TEST_SWITCHES ("name=value,name=value", handed to svo_debug_set before the context exists) and prints a digest of every
+buffer, of the id list and of the last two images (one process per combination: "main_lo" acts at context creation)."""
 import hashlib
 import os
 import sys
@@ -15,6 +15,9 @@ import scenes  # noqa: E402
 
 svo = load_package()
 svo.Device.errors_return()
+for item in filter(None, os.environ.get("SVO_TEST_SWITCHES", "").split(",")):
+    name, _, value = item.partition("=")
+    svo.ocl.debug_set(name, int(value or 1))
 mode, rx, ry, nframes = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 octree, root, _ = svo.scene.build_octree(*scenes.small_world())
 rc, ocl = svo.raycast, svo.ocl

@@ -305,7 +305,7 @@ def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
             ocl.present_wait(f & 1)
             got = np.frombuffer(host[f & 1], dtype=np.uint32).copy()
             assert np.array_equal(got, tex_ref[f]), f"frame {f} tex"
-        assert ocl.frame_deferred_count() - base == (0 if os.environ.get("SVO_NO_LAZY_COPY") else expect_deferred)
+        assert ocl.frame_deferred_count() - base == expect_deferred
         screen, back, idb = rc.read_buffers(rx, ry)
         assert rc.idbuf_size() == O.idbuf_size
         assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), "ids"
@@ -350,8 +350,8 @@ def test_present_rgb24(svo, orc, world, res):
 def test_schedule_switches(svo, mode):
     """The A/B switches of the fused frame's schedule only move work between streams and launches:
     every combination must leave bit-identical buffers, ids and images.  The default schedule is the one the other tests
-    pin against the oracle; here each switch runs the same 12 back-to-back frames in a process of its own (the switches are
-    read once per process) and its digest is compared with the default's."""
+    pin against the oracle; here each switch (svo_debug_set) runs the same 12 back-to-back frames in a process of its
+    own and its digest is compared with the default's."""
     import subprocess
     import sys
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_schedule_worker.py")
@@ -366,11 +366,10 @@ def test_schedule_switches(svo, mode):
 
     ref, deferred = run({})
     assert deferred == (10 if mode == "fused" else 0)          # frames 2..11 carried the previous frame's cache copy
-    for extra in ({"SVO_NO_SPLIT_RESOLVE": "1"}, {"SVO_NO_TILE_STAGING": "1"}, {"SVO_NO_LAZY_COPY": "1"}, {"SVO_NO_OVERLAP": "1"},
-                  {"SVO_NO_LAZY_COPY": "1", "SVO_NO_SPLIT_RESOLVE": "1"}, {"SVO_FRAME_L2_PIN": "1"}, {"SVO_MAIN_LO": "1"},
-                  {"SVO_HOLES_SMAX": "1"}):
-        got, _ = run(extra)
-        assert got == ref, f"{extra} changes the result"
+    for switches in ("no_split_resolve", "no_tile_staging", "no_lazy_copy", "no_overlap", "no_lazy_copy,no_split_resolve", "frame_l2_pin",
+                     "main_lo", "holes_smax=1", "holes_smax=32"):
+        got, _ = run({"SVO_TEST_SWITCHES": switches})
+        assert got == ref, f"{switches} changes the result"
 
 
 @pytest.mark.parametrize("mode,observe", [("reference", True), ("fused", True), ("fused", False)], ids=["reference", "fused", "fused-back-to-back"])
