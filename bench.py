@@ -644,14 +644,21 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # The NCCL communicator is created lazily (no device_id): creating it enables peer access between the GPUs, and from
+        # then on every kernel boundary of every process costs more -- the same 252 frames take 0.144 instead of 0.128 ms per
+        # frame (tools/gpu_replica_probe.sh: two independent processes on two GPUs run at full speed, the same two under an
+        # initialised NCCL communicator lose 11 %).  The view-parallel workload has no collective, so the barriers that bracket
+        # its timed regions run over a gloo group of the same ranks and NCCL first runs when the device times are reduced.
+        dist.init_process_group("nccl")
+        host_group = dist.new_group(backend="gloo") if os.environ.get("SVO_BENCH_BARRIER", "gloo") == "gloo" else None
     svo = load_package()
     if rank == 0:
         make_scene(path)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group) if host_group is not None else dist.barrier()
     octree, root, stats = svo.scene.octree_init(path)          # .rle4 loader -> direct compact-octree builder
     rc, ocl = svo.raycast, svo.ocl
     if args.bands_only:
@@ -679,7 +686,7 @@ def main():
     def sync_all():
         ocl.ocl_end_all_kernels()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=host_group) if host_group is not None else dist.barrier()
             torch.cuda.synchronize()
 
     # ---- warm-up (frames 0 and 1 are full raycasts by construction, src/raycast.h:150-154) ----
@@ -873,7 +880,10 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 120, "d2h_bytes_per_step": n * 3, "frame_format": "rgb24",
                         "ms_per_step": e2e_ms_max / args.steps, "frame_checksum": checksum, "frames_in_flight": DEPTH, "host_cpus": host_cpus,
                         "passes_fps": [round(world * args.steps / (v * 1e-3), 1) for v in e2e_passes_ms], "value_is": "median of the passes",
-                        "d2h_link_gbs": d2h_gbs, "d2h_used_gbs": e2e_fps / world * n * 3 / 1e9},
+                        "d2h_link_gbs": d2h_gbs, "d2h_used_gbs": e2e_fps / world * n * 3 / 1e9,
+                        # what the box's device -> pinned-host path allows when every rank reads back at once (the GPUs share
+                        # PCIe switches: ~55 GB/s per GPU alone, 15-20 GB/s each when 8 copy together)
+                        "link_ceiling_fps": (d2h_gbs * 1e9 / (n * 3) * world) if d2h_gbs else None},
                 "gpu_launches": launches, "host_enqueue_ms_per_frame": host_enqueue_ms, "clocks": clocks,
                 "kernel_ms_per_frame": {k: round(v, 5) for k, v in sorted(per_frame_ms.items(), key=lambda kv: -kv[1])},
                 "roofline": roof}
