@@ -600,6 +600,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the GPU output with the CPU reference (development aid)")
     ap.add_argument("--parity-frames", type=int, default=12, help="frames 0.. of the flythrough compared with the serial reference")
+    ap.add_argument("--debug-switches", default="", help="development aid: schedule A/B switches for svo_debug_set, e.g. no_split_resolve=1,holes_smax=32")
     ap.add_argument("--profile-frames", type=int, default=32)
     ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
     ap.add_argument("--ray-stripe-rows", type=int, default=16, help="stripe height of the banded full raycast at 3840x2160")
@@ -655,6 +656,9 @@ def main():
         dist.init_process_group("nccl")
         host_group = dist.new_group(backend="gloo") if os.environ.get("SVO_BENCH_BARRIER", "gloo") == "gloo" else None
     svo = load_package()
+    for item in filter(None, args.debug_switches.split(",")):
+        name, _, value = item.partition("=")
+        svo.ocl.debug_set(name, int(value or 1))
     if rank == 0:
         make_scene(path)
     if world > 1:

@@ -15,8 +15,8 @@
 //     blocks, in the same order;
 //   * colorize at the producers: gather pass, rays and gap filter store their colorized words straight into the writer
 //     rank's frame (peer stores), there is no colorize pass and no transfer pass;
-//   * the small-gap filter reads the 2 + 3 rows its 5x5 search can reach across a stripe edge straight out of the
-//     neighbour's frame (peer loads; the filter's in-place write is deferred, so the frame stays the pre-filter image);
+//   * the 2 + 3 rows the small-gap filter's 5x5 search can reach across a stripe edge are pushed into the neighbour's halo
+//     buffer by one small launch in front of barrier B2 (peer stores), so the filter itself reads only local memory;
 //   * cross-GPU ordering is a flag barrier in peer memory (k_band_barrier, one tiny launch).  Two per frame on the critical
 //     stream: B1 after the scatter (every candidate has reached its owner's keys) and B2 after the rays and the gather pass
 //     (nobody gathers from the cache rows or writes the keys any more: the next frame's scatter may overwrite them; the
@@ -45,6 +45,7 @@ struct BandPeers {                               // base pointers of every rank'
     uint32_t *screen[kMaxBands];
     float *back[kMaxBands];
     unsigned long long *key[kMaxBands];
+    uint32_t *halo[kMaxBands];                   // [frame parity][local stripe][5][res_x]: the 2 rows above and 3 rows below each stripe
     uint32_t *tex;                               // the writer's colorize target
 };
 
@@ -511,16 +512,50 @@ k_band_copy(BandMap m, BandPeers P, int src_slot, int copy_slot)
     }
 }
 
-// gap filter (raycast_fillhole2) on the listed pixels of this rank, snapshot semantics: every rank's destination slot holds
-// the pre-filter image of its rows until the next frame's gather pass (the filter's in-place write is deferred), so rows
-// of other ranks -- the 5x5 search reaches 2 rows above and 3 below a stripe -- are read straight from their owner
-// (peer loads); offsets past the image read the words that follow it in the reference's layout (`beyond`).
+// The rows of this rank's finished (pre-filter) frame that a NEIGHBOUR's gap filter can reach -- its 5x5 search looks 2 rows
+// above and 3 rows below a stripe -- pushed into that neighbour's halo buffer (peer stores): the last 2 rows of a stripe are
+// "rows above" the next stripe, the first 3 rows are "rows below" the previous one.  One small launch after the rank's rays,
+// in front of barrier B2; with it a rank's filter reads nothing but local memory, so nobody has to wait for the other
+// ranks' filters before rewriting its frame (the peer-load form of the filter put a third barrier on every frame's path).
+// Two halo sets alternate by frame: a fast neighbour may push frame f+1 while this rank's filter still reads frame f.
+__global__ void __launch_bounds__(256)
+k_band_push_halo(BandMap m, BandPeers P, int dst_slot, int parity, int local_stripes_max)
+{
+    const int res_x = m.res_x;
+    const size_t n = (size_t)res_x * m.res_y;
+    const uint32_t *__restrict__ own = P.screen[m.rank] + (size_t)dst_slot * n;
+    const int nstripes = (m.res_y + m.SR - 1) / m.SR;
+    const int mine = (nstripes - m.rank + m.G - 1) / m.G;                 // stripes this rank owns
+    const int per_stripe = 5 * res_x;                                       // rows j = 0,1,2 (for the stripe above) and SR-2, SR-1 (for the stripe below)
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < mine * per_stripe; t += gridDim.x * blockDim.x) {
+        const int k = t / per_stripe, r = (t - k * per_stripe) / res_x, x = t - k * per_stripe - r * res_x;
+        const int s = k * m.G + m.rank;                                     // global stripe
+        const int j = r < 3 ? r : m.SR - 5 + r;                             // row inside the stripe
+        const int y = s * m.SR + j;
+        if (y >= m.res_y) continue;
+        const uint32_t v = own[(size_t)y * res_x + x];
+        if (r < 3) {                                                        // first rows: below the previous stripe
+            if (s > 0) P.halo[(s - 1) % m.G][((size_t)(parity * local_stripes_max + (s - 1) / m.G) * 5 + 2 + j) * res_x + x] = v;
+        } else if (s + 1 < nstripes) {                                      // last two rows: above the next stripe
+            P.halo[(s + 1) % m.G][((size_t)(parity * local_stripes_max + (s + 1) / m.G) * 5 + (j - (m.SR - 2))) * res_x + x] = v;
+        }
+    }
+}
+
+// gap filter (raycast_fillhole2) on the listed pixels of this rank, snapshot semantics: the rank's destination slot holds the
+// pre-filter image of its rows until the next frame's gather pass (the filter's in-place write is deferred), rows of other
+// ranks come from the halo the neighbours pushed; offsets past the image read the words that follow it in the reference's
+// layout (`beyond`).
 struct BandSnapView {
-    const BandPeers *P; BandMap m; size_t slot_ofs; int n;
+    const uint32_t *own, *halo; BandMap m; int n, py;
     __device__ __forceinline__ uint32_t operator[](int i) const
     {
-        if (i >= n) return P->screen[m.rank][slot_ofs + i];
-        return P->screen[m.owner(i / m.res_x)][slot_ofs + i];
+        if (i >= n) return own[i];
+        const int row = i / m.res_x;
+        if (m.owner(row) == m.rank) return own[i];
+        const int s = py / m.SR, k = s / m.G;
+        const int slot = row < s * m.SR ? row - (s * m.SR - 2) : 2 + row - (s + 1) * m.SR;
+        return halo[((size_t)k * 5 + slot) * m.res_x + (i - row * m.res_x)];
     }
 };
 
@@ -544,14 +579,13 @@ __device__ __forceinline__ uint32_t band_fill_pixel(const BandSnapView &view, in
 }
 
 // Listed pixels whose 5x5 neighbourhood lies inside the rank's own stripe (all but the 2 + 3 rows at its edges) read the
-// rank's frame directly (fillhole2_view: every load issued before the first test); the edge rows go through the peer view.
+// rank's frame directly (fillhole2_view: every load issued before the first test); the edge rows go through the halo view.
 __global__ void __launch_bounds__(256)
-k_band_fill_list(BandMap m, BandPeers P, int dst_slot, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid,
-                 const unsigned int *__restrict__ resid_count, PatchList patch)
+k_band_fill_list(BandMap m, const uint32_t *__restrict__ own, const uint32_t *__restrict__ halo, uint32_t *__restrict__ tex,
+                 const uint32_t *__restrict__ resid, const unsigned int *__restrict__ resid_count, PatchList patch)
 {
     const unsigned int cnt = resid_count[0];
     const int n = m.res_x * m.res_y;
-    const uint32_t *__restrict__ own = P.screen[m.rank] + (size_t)dst_slot * n;
     const SnapView local = {own, own, n};
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int p = (int)resid[i];
@@ -560,7 +594,7 @@ k_band_fill_list(BandMap m, BandPeers P, int dst_slot, uint32_t *__restrict__ te
         uint32_t f;
         if (m.G == 1 || (j >= 2 && j < m.SR - 3 && y + 3 < m.res_y)) f = fillhole2_view(local, p, m.res_x);
         else {
-            const BandSnapView view = {&P, m, (size_t)dst_slot * n, n};
+            const BandSnapView view = {own, halo, m, n, y};
             f = band_fill_pixel(view, p, m.res_x);
         }
         patch.value[p] = f;

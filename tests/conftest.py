@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# "virtual" band sets put up to 8 bands (8 contexts, 4 streams each) on one device and synchronise them with spinning flag
+# barriers: give the device its maximum of hardware launch queues so that two bands' streams do not share one (must be set
+# before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
