@@ -86,9 +86,12 @@ __global__ void k_band_barrier(BandFlags f, int rank, int G, uint32_t epoch, uns
 // thread -- the colour words as one uint4, the positions as four float4, all issued before the first use -- and no integer
 // division per pixel.  Remote candidates are plain fire-and-forget reductions on the owner's key (NVLink atomics); the
 // launch boundary plus the barrier's system-scope release order them before any rank reads its keys.
-// (Tried: the barrier behind this pass folded into the kernels on either side of it -- the last CTA here signals, every CTA of
-// the id pass waits in its prologue.  It saves a launch and loses 10 % of the frame at 2 GPUs: the waiting grid holds the SMs'
-// CTA slots, the gap filter of the previous frame starves on its low-priority stream, and every rank's hole rays wait for it.)
+// (Tried twice: the barrier behind this pass folded into the kernels around it.  (1) The last CTA here signals, every CTA of
+// the id pass waits in its prologue: one launch less, -10 % at 2 GPUs -- the waiting grid holds the SMs' CTA slots and the
+// previous frame's gap filter starves.  (2) Only the signal folded in (last-CTA detection: every CTA fences at system scope
+// and bumps a counter), the wait a one-warp launch, and B2 likewise inside the halo push: -23 % at 2 GPUs -- a system-scope
+// fence at the end of every CTA waits for that CTA's NVLink reductions to be acknowledged and stalls this HBM-bound pass.
+// The barrier stays a launch of its own: the launch boundary orders the remote traffic for free.)
 __global__ void __launch_bounds__(256)
 k_band_scatter(BandMap m, BandPeers P, unsigned int *__restrict__ next_resid_count, int slot0, int copy_slot,
                unsigned int key_bias, ProjCam c)
