@@ -529,19 +529,24 @@ k_band_push_halo(BandMap m, BandPeers P, int dst_slot, int parity, int local_str
     const uint32_t *__restrict__ own = P.screen[m.rank] + (size_t)dst_slot * n;
     const int nstripes = (m.res_y + m.SR - 1) / m.SR;
     const int mine = (nstripes - m.rank + m.G - 1) / m.G;                 // stripes this rank owns
-    const int per_stripe = 5 * res_x;                                       // rows j = 0,1,2 (for the stripe above) and SR-2, SR-1 (for the stripe below)
+    const bool vec = (res_x & 3) == 0;                                      // four pixels (one 16-byte peer store) per thread
+    const int qpr = vec ? res_x >> 2 : res_x, per_stripe = 5 * qpr;         // rows j = 0,1,2 (for the stripe above) and SR-2, SR-1 (for the stripe below)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < mine * per_stripe; t += gridDim.x * blockDim.x) {
-        const int k = t / per_stripe, r = (t - k * per_stripe) / res_x, x = t - k * per_stripe - r * res_x;
+        const int k = t / per_stripe, r = (t - k * per_stripe) / qpr, xq = t - k * per_stripe - r * qpr;
+        const int x = vec ? xq * 4 : xq;
         const int s = k * m.G + m.rank;                                     // global stripe
         const int j = r < 3 ? r : m.SR - 5 + r;                             // row inside the stripe
         const int y = s * m.SR + j;
         if (y >= m.res_y) continue;
-        const uint32_t v = own[(size_t)y * res_x + x];
+        uint32_t *dst = nullptr;
         if (r < 3) {                                                        // first rows: below the previous stripe
-            if (s > 0) P.halo[(s - 1) % m.G][((size_t)(parity * local_stripes_max + (s - 1) / m.G) * 5 + 2 + j) * res_x + x] = v;
+            if (s > 0) dst = P.halo[(s - 1) % m.G] + ((size_t)(parity * local_stripes_max + (s - 1) / m.G) * 5 + 2 + j) * res_x + x;
         } else if (s + 1 < nstripes) {                                      // last two rows: above the next stripe
-            P.halo[(s + 1) % m.G][((size_t)(parity * local_stripes_max + (s + 1) / m.G) * 5 + (j - (m.SR - 2))) * res_x + x] = v;
+            dst = P.halo[(s + 1) % m.G] + ((size_t)(parity * local_stripes_max + (s + 1) / m.G) * 5 + (j - (m.SR - 2))) * res_x + x;
         }
+        if (!dst) continue;
+        if (vec) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(own + (size_t)y * res_x + x);
+        else *dst = own[(size_t)y * res_x + x];
     }
 }
 
