@@ -150,6 +150,11 @@ int  svo_frame_last_slot(void);
  * every observation finds buffer 2 as the reference leaves it.  Diagnostic: lets a test prove which schedule produced
  * the buffers it compares. */
 unsigned long long svo_frame_deferred_count(void);
+/* Number of those frames whose reprojection additionally ran EARLY: as a pass on a stream of its own right behind the
+ * previous frame's gather pass -- beside that frame's hole rays, with the 2x2 cells they were still tracing masked out --
+ * plus a list pass over exactly those cells once the rays were done (same keys, same buffer 2: the depth test is an
+ * order-independent atomicMin and every pixel is copied and projected once).  Diagnostic, like the counter above. */
+unsigned long long svo_frame_early_count(void);
 
 /* ---- screen bands across the GPUs of one box (extension: the reference is single-device, src/ocl.h:89,127,140) ----
  * The screen is cut into stripes of `stripe_rows` rows (rounded up to a multiple of the 16-row hole block; <= 0 selects

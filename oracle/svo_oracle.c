@@ -272,6 +272,11 @@ int orc_write_rle4(const char *path, int sx, int sy, int sz, size_t nslabs, cons
 static uint64_t g_rays, g_iters, g_loads;
 static uint32_t *g_iter_buf = NULL;     /* optional per-pixel iteration counts (analysis of ray-length tails) */
 void orc_set_iter_buffer(uint32_t *buf) { g_iter_buf = buf; }
+/* optional per-pixel trip log (tools/warp_sim.py: lane-occupancy model of the GPU's while-while loop): `stride` bytes per
+ * pixel; byte k = descents the ray makes before its k-th step, bit 7 set on the ray's last entry (hit or exit). */
+static uint8_t *g_trip_log = NULL;
+static int g_trip_stride = 0;
+void orc_set_trip_log(uint8_t *buf, int stride) { g_trip_log = buf; g_trip_stride = stride; }
 void orc_stats_reset(void) { g_rays = g_iters = g_loads = 0; }
 void orc_stats(uint64_t *rays, uint64_t *iterations, uint64_t *octree_loads)
 {
@@ -285,6 +290,7 @@ typedef struct {
     int rekursion;
     float px, py, pz;        /* un-mirrored ray position in kernel units */
     uint32_t iters, loads;
+    uint8_t *trips;          /* analysis only: see orc_set_trip_log */
 } RayState;
 
 /* kernel/kernel.cl:32-62.  Three encodings: normal node -> direct index;
@@ -374,6 +380,8 @@ static void cast_ray(const uint32_t *oct, uint32_t root, float ox, float oy, flo
     int x0ry = 0;
     const int sign_xyz = sign_x | (sign_y << 1) | (sign_z << 2);
     uint32_t iters = 0, loads = 0;
+    int trip = 0, desc = 0;
+    uint8_t *const trips = r->trips;
 
     do {
         ++iters;
@@ -384,6 +392,7 @@ static void cast_ray(const uint32_t *oct, uint32_t root, float ox, float oy, flo
             const uint32_t tmp = nodeid;
             nodeid = fetch_child(oct, nodeid, nodeid_before, &local_root, (uint32_t)node_index, node_test, rekursion, &loads);
             nodeid_before = tmp;
+            ++desc;
             if (rekursion <= lod) break;                /* hit :172 */
             rekursion--;
             stack[rekursion] = nodeid;
@@ -394,6 +403,8 @@ static void cast_ray(const uint32_t *oct, uint32_t root, float ox, float oy, flo
         const float my = (float)((cy + 1) << rekursion) - py;
         const float mz = (float)((cz + 1) << rekursion) - pz;
         const int bx = (int)px, by = (int)py, bz = (int)pz;          /* raypos_before :184 */
+        if (trips && trip < g_trip_stride - 1) trips[trip++] = (uint8_t)(desc < 127 ? desc : 127);
+        desc = 0;
         float dist = mx * len0;
         float sx = 1.0f * mx, sy = g0y * mx, sz = g0z * mx;          /* grad0*mul0.x */
         const float dist_y = my * len1, dist_z = mz * len2;
@@ -414,6 +425,7 @@ static void cast_ray(const uint32_t *oct, uint32_t root, float ox, float oy, flo
         if (distance > lodswitch) { lodswitch *= 2; ++lod; }         /* :209 */
     } while (!(x0ry & (2 * DEPTH_AND + 2)));                         /* :211: y left [0, SCALE_MAX) */
 
+    if (trips) { if (desc || !trip) trips[trip++] = (uint8_t)desc; trips[trip - 1] |= 0x80; }
     if (sign_x) px = (float)SCALE_MAX - px;
     if (sign_y) py = (float)SCALE_MAX - py;
     if (sign_z) pz = (float)SCALE_MAX - pz;
@@ -435,6 +447,7 @@ static void shade_pixel(uint32_t *screen, float *back, const uint32_t *oct, uint
     const float dy = d1x * my[0] + d1y * my[1] + d1z * my[2];
     const float dz = d1x * mz[0] + d1y * mz[1] + d1z * mz[2];
     RayState r;
+    r.trips = g_trip_log ? g_trip_log + ((size_t)idy * res_x + idx) * g_trip_stride : NULL;
     cast_ray(oct, root, m0[0] * 16.0f, m0[1] * 16.0f, m0[2] * 16.0f, dx, dy, dz, (float)(res_x * LOD_ADJUST * 2), &r);
     const uint32_t col = fetch_color(oct, r.nodeid, r.nodeid_before, r.node_before2, &r.local_root,
                                      r.rekursion, r.node_test, &r.loads);

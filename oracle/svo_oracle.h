@@ -32,6 +32,7 @@ int      orc_max_threads(void);
 
 /* instrumentation of the ray kernels: totals since the last orc_stats_reset() */
 void     orc_set_iter_buffer(uint32_t *per_pixel_iterations);   /* NULL = off */
+void     orc_set_trip_log(uint8_t *per_pixel_log, int stride);   /* NULL = off; analysis only (tools/warp_sim.py) */
 void     orc_stats_reset(void);
 void     orc_stats(uint64_t *rays, uint64_t *iterations, uint64_t *octree_loads);
 

@@ -27,6 +27,15 @@ struct svo_ctx_s {
     cudaEvent_t ev_scatter_done = nullptr, ev_rays_done = nullptr;
     cudaStream_t stream4 = nullptr;         // split resolve: the gather pass runs here, beside the hole rays
     cudaEvent_t ev_ids_done = nullptr, ev_gather_done = nullptr;
+    // early reprojection: the next frame's reprojection pass runs on stream5 right behind this frame's gather pass, beside the
+    // hole rays, with the cells they are still tracing masked out (cell_mask, written by k_hole_ids); k_list_scatter follows
+    cudaStream_t stream5 = nullptr;
+    cudaEvent_t ev_early_done = nullptr;
+    uint8_t *cell_mask = nullptr; size_t cell_mask_bytes = 0;
+    bool early_ready = false;               // the last fused frame left a mask + id list that describe its pending cells
+    int early_res_x = 0, early_res_y = 0;
+    const uint32_t *early_idb = nullptr;
+    uint64_t frames_early = 0;              // frames whose reprojection ran as early pass + list pass
     uint32_t *stage_s = nullptr; float *stage_b = nullptr;   // tile-ray staging (same pixel offsets as a frame; only the tile is touched)
     size_t stage_pixels = 0;
     bool copy_pending = false;              // buffer 2 does not yet hold the last frame (materialize_copy)

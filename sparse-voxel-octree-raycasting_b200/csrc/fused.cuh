@@ -141,7 +141,8 @@ constexpr int kScatterPix = SVO_SCATTER_PIX;
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
                 int res_x, int res_y, unsigned int src0, unsigned int nsrc, unsigned int key_bias, ProjCam c,
-                uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b, uint32_t *mark = nullptr)
+                uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b, uint32_t *mark = nullptr,
+                const uint8_t *__restrict__ skip_cells = nullptr, int cells_w = 0)
 {
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int q0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,6 +151,10 @@ k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ b
     for (int i = 0; i < kScatterPix; ++i) {
         const unsigned int q = q0 + i * stride;
         live[i] = q < nsrc;
+        if (skip_cells && live[i]) {                     // early pass: the hole rays still own these 2x2 cells (k_list_scatter follows)
+            const unsigned int y = q / (unsigned int)res_x, x = q - y * (unsigned int)res_x;
+            live[i] = skip_cells[(size_t)(y >> 1) * cells_w + (x >> 1)] == 0;
+        }
         word[i] = kHole; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live[i]) {
             word[i] = ld_stream(screen + q + src0);
@@ -169,6 +174,34 @@ k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ b
             continue;
         }
         atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (q + src0 + key_bias));
+    }
+}
+
+// Early reprojection (svo_frame_fused, steady state).  After the gather pass of frame f every pixel of buffer 0 is final
+// except the 2x2 cells the hole rays of frame f are still tracing.  The reprojection (+ carried cache copy) of frame f+1
+// therefore starts right behind that gather pass, on a stream of its own and BESIDE the hole rays -- the longest link of
+// the frame's chain -- with those cells masked out (`skip_cells`, one byte per 2x2 cell, written by k_hole_ids of frame f);
+// this kernel does the same for the pixels of the masked cells, taken from frame f's hole index list, once the rays are
+// done.  atomicMin is order-independent and every pixel is copied and projected exactly once, so keys and buffer 2 are the
+// ones the single pass leaves.
+__global__ void __launch_bounds__(256)
+k_list_scatter(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
+               int res_x, int res_y, const uint32_t *__restrict__ idb, unsigned int list_ofs, unsigned int key_bias, ProjCam c,
+               uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b)
+{
+    const unsigned int total = idb[0];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t idxy = idb[list_ofs + i];
+        const int x = (int)(idxy & 0xffffu), y = (int)(idxy >> 16);
+        if (x >= res_x || y >= res_y) continue;          // (the hole rays' guard, kernel.cl:628)
+        const unsigned int q = (unsigned int)y * (unsigned int)res_x + (unsigned int)x;
+        const uint32_t word = screen[q];
+        const float4 pc = *reinterpret_cast<const float4 *>(back + (size_t)q * 4);
+        copy_s[q] = word; copy_b[q] = pc;
+        if (word == kHole) continue;
+        int sx, sy; float phz;
+        if (!proj_point_fast(c, pc.x, pc.y, pc.z, res_x, res_y, sx, sy, phz)) continue;
+        atomicMin(key + (size_t)sy * res_x + sx, ((unsigned long long)proj_sz(phz) << 32) | (q + key_bias));
     }
 }
 
@@ -313,16 +346,6 @@ k_resolve_gather(const GatherArgs a)
                 }
             }
             const bool staged = a.stage_s != nullptr;
-            uint32_t scol[4] = {0, 0, 0, 0}; float4 spc[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                spc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (staged && inr[i] && !(!IDS && hole)) {
-                    const size_t q = pp[i >> 1] + (i & 1);
-                    scol[i] = ld_stream(a.stage_s + q);
-                    spc[i] = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + q * 4));      // w unused
-                }
-            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t p = pp[r];
@@ -342,9 +365,12 @@ k_resolve_gather(const GatherArgs a)
                         else *reinterpret_cast<float4 *>(dback + (p + j) * 4) = make_float4(pc[i].x, pc[i].y, pc[i].z, phz);
                     }
                     if (staged && inr[i] && !(!IDS && hole)) {               // ... from the staging buffers
-                        out[j] = scol[i];
-                        *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc[i].x, spc[i].y);
-                        dback[(p + j) * 4 + 2] = spc[i].z;
+                        // (1/32 of the screen: loaded here, not held in registers across the gathers -- the register budget
+                        // decides how many CTAs of this pass fit beside the resident hole-ray CTAs)
+                        const float4 spc = ld_stream(reinterpret_cast<const float4 *>(a.stage_b + (p + j) * 4));      // w unused
+                        out[j] = ld_stream(a.stage_s + p + j);
+                        *reinterpret_cast<float2 *>(dback + (p + j) * 4) = make_float2(spc.x, spc.y);
+                        dback[(p + j) * 4 + 2] = spc.z;
                     }
                 }
                 if (!IDS && hole) continue;                              // the hole rays own this cell
@@ -441,7 +467,8 @@ k_resolve_gather(const GatherArgs a)
 constexpr int kIdsBlocksPerCta = 2 * kGatherBlocksPerCta;
 
 __global__ void __launch_bounds__(256)
-k_hole_ids(const unsigned long long *__restrict__ key, uint32_t *__restrict__ idb, FusedScratch s, uint32_t epoch, int res_x, int res_y)
+k_hole_ids(const unsigned long long *__restrict__ key, uint32_t *__restrict__ idb, FusedScratch s, uint32_t epoch, int res_x, int res_y,
+           uint8_t *__restrict__ cell_mask = nullptr, int cells_w = 0)
 {
     __shared__ unsigned int ticket_s;
     __shared__ uint32_t warp_cnt[2][8];
@@ -482,6 +509,8 @@ k_hole_ids(const unsigned long long *__restrict__ key, uint32_t *__restrict__ id
         hole[c] = active[c] && !key_valid(k[c][0]) && !key_valid(k[c][1]) && !key_valid(k[c][2]) && !key_valid(k[c][3]);
         m[c] = __ballot_sync(0xffffffffu, hole[c]);
         if (lane == 0) warp_cnt[c][warp] = 4u * (uint32_t)__popc(m[c]);
+        // the cells the hole rays will fill, for the next frame's early reprojection pass (k_proj_scatter2 skip_cells)
+        if (cell_mask && active[c]) cell_mask[(size_t)(y[c] >> 1) * cells_w + (x[c] >> 1)] = hole[c] ? 1 : 0;
     }
     __syncthreads();
     uint32_t cta_total = 0, before_me[2] = {0, 0}, my_cnt[2];

@@ -37,7 +37,7 @@ static svo_ctx_t g_ctx = nullptr;           // current context (the reference's 
 // svo_debug_set() is the only way in; a build with -DSVO_NO_DEBUG_SWITCHES compiles them to constants.
 struct SvoDebug {
     bool no_overlap = false, no_lazy_copy = false, no_split_resolve = false, no_tile_staging = false;
-    bool frame_l2_pin = false, no_l2_pin = false, main_lo = false, band_no_tex = false;
+    bool frame_l2_pin = false, no_l2_pin = false, main_lo = false, band_no_tex = false, no_early_scatter = false, no_tile_early = false;
     int holes_smax = 8;
 };
 #ifdef SVO_NO_DEBUG_SWITCHES
@@ -57,6 +57,8 @@ extern "C" int svo_debug_set(const char *name, int value)
     else if (n == "no_l2_pin") g_dbg.no_l2_pin = value != 0;
     else if (n == "main_lo") g_dbg.main_lo = value != 0;            // before svo_init / svo_ctx_create
     else if (n == "band_no_tex") g_dbg.band_no_tex = value != 0;
+    else if (n == "no_early_scatter") g_dbg.no_early_scatter = value != 0;
+    else if (n == "no_tile_early") g_dbg.no_tile_early = value != 0;
     else if (n == "holes_smax") g_dbg.holes_smax = value > 0 ? value : 8;
     else return -1;
     return 0;
@@ -142,6 +144,8 @@ extern "C" svo_ctx_t svo_ctx_create(int device)
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_gather_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_scatter_done, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&c->ev_rays_done, cudaEventDisableTiming));
+    CU_CHECK(cudaStreamCreateWithPriority(&c->stream5, cudaStreamNonBlocking, prio_hi));
+    CU_CHECK(cudaEventCreateWithFlags(&c->ev_early_done, cudaEventDisableTiming));
     c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     g_live_ctx.push_back(c);
@@ -168,6 +172,10 @@ extern "C" void svo_ctx_destroy(svo_ctx_t c)
     cudaEventDestroy(c->ev_ids_done); cudaEventDestroy(c->ev_gather_done);
     if (c->stage_s) cudaFree(c->stage_s);
     if (c->stage_b) cudaFree(c->stage_b);
+    cudaStreamSynchronize(c->stream5);
+    cudaStreamDestroy(c->stream5);
+    cudaEventDestroy(c->ev_early_done);
+    if (c->cell_mask) cudaFree(c->cell_mask);
     cudaEventDestroy(c->ev_frame_done); cudaEventDestroy(c->ev_tile_done);
     cudaEventDestroy(c->ev_copy_done); cudaEventDestroy(c->ev_fill_done);
     if (c->patch.value) cudaFree(c->patch.value);
@@ -239,7 +247,7 @@ extern "C" void svo_free(svo_mem_t m)
     if (owner) {
         cudaSetDevice(owner->device);
         flush_patches(owner);
-        for (cudaStream_t st : {owner->stream, owner->stream2, owner->stream3, owner->stream4}) cudaStreamSynchronize(st);
+        for (cudaStream_t st : {owner->stream, owner->stream2, owner->stream3, owner->stream4, owner->stream5}) cudaStreamSynchronize(st);
         if (owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
     }
     cudaFree(m->dptr);
@@ -398,6 +406,7 @@ static void prof_flush(svo_ctx_t c)
     CU_CHECK(cudaStreamSynchronize(c->stream2));
     CU_CHECK(cudaStreamSynchronize(c->stream3));
     CU_CHECK(cudaStreamSynchronize(c->stream4));
+    CU_CHECK(cudaStreamSynchronize(c->stream5));
     c->timeline.clear();
     for (auto &r : c->prof_pending) {
         float ms = 0.f, t0 = 0.f;
@@ -871,6 +880,7 @@ extern "C" void svo_end_all_kernels(void)                             // src/ocl
     CU_CHECK(cudaStreamSynchronize(c->stream2));
     CU_CHECK(cudaStreamSynchronize(c->stream3));
     CU_CHECK(cudaStreamSynchronize(c->stream4));
+    CU_CHECK(cudaStreamSynchronize(c->stream5));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -969,12 +979,26 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const bool staged = split && stage_tile;
     if (staged && c->stage_pixels < n) {
         if (c->stage_s) {
-            for (cudaStream_t st : {c->stream, c->stream2, c->stream3, c->stream4}) CU_CHECK(cudaStreamSynchronize(st));
+            for (cudaStream_t st : {c->stream, c->stream2, c->stream3, c->stream4, c->stream5}) CU_CHECK(cudaStreamSynchronize(st));
             CU_CHECK(cudaFree(c->stage_s)); CU_CHECK(cudaFree(c->stage_b));
         }
         CU_CHECK(cudaMalloc(&c->stage_s, (size_t)n * 4));
         CU_CHECK(cudaMalloc(&c->stage_b, (size_t)n * 16));
         c->stage_pixels = n;
+    }
+    // Early reprojection (fused.cuh, k_list_scatter): when this frame carries the previous frame's copy (from0) and that
+    // frame left its pending-cell mask + id list, the reprojection runs as an early pass on stream5 -- right behind the
+    // previous frame's gather pass, beside its hole rays -- plus a list pass over the hole rays' pixels on the main stream.
+    const int cells_w = (res_x + 1) / 2;
+    const size_t mask_bytes = (size_t)cells_w * ((res_y + 1) / 2);
+    const bool early_capable = split && staged && lazy && !rotate && nb > 0 && !g_dbg.no_early_scatter;
+    const bool early = early_capable && from0 && c->early_ready && c->early_res_x == res_x && c->early_res_y == res_y &&
+                       c->early_idb == idb;
+    if (early_capable && c->cell_mask_bytes < mask_bytes) {                // (never while an early pass could be reading it: !early here)
+        if (c->cell_mask) { for (cudaStream_t st : {c->stream, c->stream5}) CU_CHECK(cudaStreamSynchronize(st)); CU_CHECK(cudaFree(c->cell_mask)); }
+        CU_CHECK(cudaMalloc(&c->cell_mask, mask_bytes));
+        CU_CHECK(cudaMemsetAsync(c->cell_mask, 0, mask_bytes, c->stream));  // cells outside the whole 16x16 blocks stay 0
+        c->cell_mask_bytes = mask_bytes;
     }
     auto launch_tile = [&](cudaStream_t st) {                              // :361-387 tile refresh
         LAUNCH_ON(c, "k_rays_tile", st);
@@ -998,13 +1022,36 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         // the tile rays depend on nothing of this frame: start them first (second stream, behind what the main stream has
         // done so far), concurrently with the reprojection
         if (!staged) join_fill();                                          // (the filter reads the destination)
-        CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
-        CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
+        if (early && !g_dbg.no_tile_early) {
+            // staged tile rays need nothing but the camera and the staging buffers, which the previous frame's gather pass
+            // has finished reading: they may start beside that frame's hole rays, like the early reprojection pass
+            CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_gather_done, 0));
+        } else {
+            CU_CHECK(cudaEventRecord(c->ev_frame_done, c->stream));
+            CU_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_frame_done, 0));
+        }
         launch_tile(c->stream2);
         CU_CHECK(cudaEventRecord(c->ev_tile_done, c->stream2));
         tile_launched = true;
     }
-    if (!rotate) {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
+    if (early) {     // :177-198 (+ :394-405 of the previous frame) in two parts, see above
+        // ev_gather_done: the previous frame's gather pass has written every pixel but the pending cells, has re-armed the
+        // keys and no longer reads buffer 2 (it follows that frame's id pass and tile rays, so those are done too)
+        CU_CHECK(cudaStreamWaitEvent(c->stream5, c->ev_gather_done, 0));
+        {
+            LAUNCH_ON(c, "k_proj_scatter2", c->stream5);
+            k_proj_scatter2<<<(n + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream5>>>(screen, back, c->key, res_x, res_y, 0u, n, 2u * n, pc,
+                screen + 2 * (size_t)n, reinterpret_cast<float4 *>(back) + 2 * (size_t)n, nullptr, c->cell_mask, cells_w);
+        }
+        CU_CHECK(cudaEventRecord(c->ev_early_done, c->stream5));
+        CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev_early_done, 0));
+        {   // main stream: behind the previous frame's hole rays
+            LAUNCH(c, "k_list_scatter");
+            k_list_scatter<<<64, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, idb, 2u * (unsigned int)nb, 2u * n, pc,
+                                                      screen + 2 * (size_t)n, reinterpret_cast<float4 *>(back) + 2 * (size_t)n);
+        }
+        c->frames_early++;
+    } else if (!rotate) {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = from0 ? n : (unsigned int)src_count * n;
         k_proj_scatter2<<<(nsrc + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
@@ -1040,7 +1087,8 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     if (split) {
         if (nb) {   // :272-315 hole gather from the keys alone, ids in the reference's order, idb[0] = idbuf_size
             LAUNCH(c, "k_hole_ids");
-            k_hole_ids<<<(unsigned)((nb + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta), 256, 0, c->stream>>>(c->key, idb, fs, c->epoch, res_x, res_y);
+            k_hole_ids<<<(unsigned)((nb + kIdsBlocksPerCta - 1) / kIdsBlocksPerCta), 256, 0, c->stream>>>(c->key, idb, fs, c->epoch, res_x, res_y,
+                                                                                                          early_capable ? c->cell_mask : nullptr, cells_w);
         } else CU_CHECK(cudaMemsetAsync(idb, 0, 4, c->stream));              // no whole 16x16 block: idbuf_size = 0
         CU_CHECK(cudaEventRecord(c->ev_ids_done, c->stream));
         CU_CHECK(cudaStreamWaitEvent(c->stream4, c->ev_ids_done, 0));                             // (re-arms the keys the id pass reads)
@@ -1098,6 +1146,8 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         c->patch_count = fs.resid_count;
         c->patch_resid = fs.resid;
     }
+    c->early_ready = early_capable;                                        // mask + id list of this frame describe its pending cells
+    c->early_res_x = res_x; c->early_res_y = res_y; c->early_idb = idb;
     c->last_slot = dst_slot;
     c->have_frame = true;
     c->last_idbuf = idbuffer;
@@ -1135,6 +1185,7 @@ extern "C" void svo_raycast_batch(svo_mem_t screenbuffer, svo_mem_t backbuffer, 
 
 extern "C" int svo_frame_last_slot(void) { return g_ctx ? g_ctx->last_slot : 0; }
 extern "C" unsigned long long svo_frame_deferred_count(void) { return g_ctx ? g_ctx->frames_from0 : 0ull; }
+extern "C" unsigned long long svo_frame_early_count(void) { return g_ctx ? g_ctx->frames_early : 0ull; }
 
 extern "C" int svo_frame_idbuf_size(void)
 {

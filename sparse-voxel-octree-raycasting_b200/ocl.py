@@ -74,6 +74,7 @@ _svo_raycast_batch = _sig("svo_raycast_batch", None, _vp, _vp, _vp, _u32, _i, _i
 _svo_frame_idbuf_size = _sig("svo_frame_idbuf_size", _i)
 _svo_frame_last_slot = _sig("svo_frame_last_slot", _i)
 _svo_frame_deferred_count = _sig("svo_frame_deferred_count", C.c_uint64)
+_svo_frame_early_count = _sig("svo_frame_early_count", C.c_uint64)
 
 _svo_event_record = _sig("svo_event_record", None, _i)
 _svo_event_elapsed_ms = _sig("svo_event_elapsed_ms", C.c_float, _i, _i)
@@ -275,6 +276,11 @@ def frame_last_slot():
 def frame_deferred_count():
     """Fused frames whose reprojection pass carried the previous frame's cache copy (see svo_frame_deferred_count)."""
     return int(_svo_frame_deferred_count())
+
+
+def frame_early_count():
+    """Of those, the frames whose reprojection ran as early pass + list pass (see svo_frame_early_count)."""
+    return int(_svo_frame_early_count())
 
 
 def frame_idbuf_size():

@@ -287,7 +287,7 @@ def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
                 obs_ref[f] = O.screen[:n].copy()
             rc.set_camera(pos, rot)
             params.append(rc.prepare_params(rx, ry, f))
-        base = ocl.frame_deferred_count()
+        base, base_early = ocl.frame_deferred_count(), ocl.frame_early_count()
         expect_deferred = 0
         for f in range(nframes):
             if f >= 2:                                   # the caller owns host[f & 1] again: frame f-2 has landed
@@ -306,6 +306,8 @@ def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
             got = np.frombuffer(host[f & 1], dtype=np.uint32).copy()
             assert np.array_equal(got, tex_ref[f]), f"frame {f} tex"
         assert ocl.frame_deferred_count() - base == expect_deferred
+        # ... and every one of them ran its reprojection as early pass (beside the previous frame's hole rays) + list pass
+        assert ocl.frame_early_count() - base_early == expect_deferred
         screen, back, idb = rc.read_buffers(rx, ry)
         assert rc.idbuf_size() == O.idbuf_size
         assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), "ids"
@@ -367,7 +369,7 @@ def test_schedule_switches(svo, mode):
     ref, deferred = run({})
     assert deferred == (10 if mode == "fused" else 0)          # frames 2..11 carried the previous frame's cache copy
     for switches in ("no_split_resolve", "no_tile_staging", "no_lazy_copy", "no_overlap", "no_lazy_copy,no_split_resolve", "frame_l2_pin",
-                     "main_lo", "holes_smax=1", "holes_smax=32"):
+                     "main_lo", "holes_smax=1", "holes_smax=32", "no_early_scatter", "no_early_scatter,holes_smax=32", "no_tile_early"):
         got, _ = run({"SVO_TEST_SWITCHES": switches})
         assert got == ref, f"{switches} changes the result"
 
