@@ -131,6 +131,59 @@ def sim_refill(desc, ntrips, rx, ry, thresh, strip, fw=8, fh=4, converged_setup=
     return wi, ti, nrays
 
 
+def sim_policies(desc, ntrips, rx, ry, nwarps=4000, fw=8, fh=4):
+    """Which phase a warp runs when its lanes disagree.  Every ray is a string of actions (D = descent iteration, S = step);
+    per warp iteration the policy picks the action(s) to issue, lanes whose next action matches advance.  Vectorised over a
+    random sample of warps.  Returns {policy: (warp instructions per ray, lanes per instruction)}."""
+    d = desc.reshape(ry // fh, fh, rx // fw, fw, -1).transpose(0, 2, 1, 3, 4).reshape(-1, 32, desc.shape[1])
+    nt = ntrips.reshape(ry // fh, fh, rx // fw, fw).transpose(0, 2, 1, 3).reshape(-1, 32)
+    sel = np.random.default_rng(0).choice(d.shape[0], min(nwarps, d.shape[0]), replace=False)
+    d, nt = d[sel], nt[sel]
+    W, T, L = d.shape[0], d.shape[2], 640
+    trip = np.arange(T)[None, None, :]
+    alive = trip < nt[:, :, None]
+    d = np.where(alive, d, 0)
+    has_step = alive & ~((trip == (nt[:, :, None] - 1)) & (d > 0))
+    cs = np.cumsum(d, axis=2)
+    pos_s = cs + np.cumsum(has_step, axis=2) - has_step                 # position of trip k's step in the action string
+    length = cs[:, :, -1] + has_step.sum(axis=2)
+    act = np.full((W, 32, L), 2, np.int8)                               # 0 = D, 1 = S, 2 = done
+    act[np.arange(L)[None, None, :] < length[:, :, None]] = 0
+    w_i, l_i, t_i = np.nonzero(has_step)
+    p = pos_s[w_i, l_i, t_i]
+    ok = p < L
+    act[w_i[ok], l_i[ok], p[ok]] = 1
+    wI, lI = np.arange(W)[:, None], np.arange(32)[None, :]
+    out = {}
+    for policy in ("descents first (today)", "steps first", "if-if", "majority", "descend while >= 12 lanes"):
+        ptr = np.zeros((W, 32), np.int64)
+        wi = np.zeros(W)
+        ti = np.zeros(W)
+        while True:
+            a = act[wI, lI, np.minimum(ptr, L - 1)]
+            wd, wsx = a == 0, a == 1
+            nd, ns = wd.sum(1), wsx.sum(1)
+            if not ((nd + ns) > 0).any():
+                break
+            if policy.startswith("descents"):
+                do_d = nd > 0; do_s = (nd == 0) & (ns > 0)
+            elif policy.startswith("steps"):
+                do_s = ns > 0; do_d = (ns == 0) & (nd > 0)
+            elif policy == "if-if":
+                do_d = nd > 0; do_s = ns > 0
+            elif policy == "majority":
+                do_d = (nd > 0) & (nd >= ns); do_s = (ns > 0) & ~do_d
+            else:
+                do_d = (nd >= 12) | ((ns == 0) & (nd > 0)); do_s = ~do_d & (ns > 0)
+            wi += do_d * C_DESC + do_s * C_STEP
+            ti += do_d * nd * C_DESC + do_s * ns * C_STEP
+            ptr += (wd & do_d[:, None]) | (wsx & do_s[:, None])
+        n = W * 32
+        wi_t, ti_t = wi.sum() + W * (C_SETUP + C_FINAL), ti.sum() + n * (C_SETUP + C_FINAL)
+        out[policy] = (wi_t / n, ti_t / wi_t)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", default="1920x1024")
@@ -144,6 +197,8 @@ def main():
     wi, ti = sim_static(desc, ntrips, rx, ry)
     print(f"static   : {wi/n:7.1f} warp inst/ray, {ti/wi:5.1f} lanes/inst")
     base = wi / n
+    for pol, (w, l) in sim_policies(desc, ntrips, rx, ry).items():
+        print(f"policy {pol:28s}: {w:7.1f} warp inst/ray, {l:5.1f} lanes/inst")
     for conv in (False, True):
         for strip in (8, 30):
             for thresh in (8, 16, 24, 28):
