@@ -138,23 +138,25 @@ constexpr int kScatterPix = SVO_SCATTER_PIX;
 // `mark` != nullptr (rotating cache target, SVO_FRAME_CACHE_ROTATION): these sources survive the frame -- they are not the
 // buffer the end-of-frame copy overwrites -- so the reference's store "source left the view -> hole" (kernel.cl:559-562) is
 // observable in later frames and is issued: into the copy when this pass makes one, else in place (`mark` = the source buffer).
+template <bool MASKED = false>
 __global__ void __launch_bounds__(256)
 k_proj_scatter2(const uint32_t *__restrict__ screen, const float *__restrict__ back, unsigned long long *__restrict__ key,
                 int res_x, int res_y, unsigned int src0, unsigned int nsrc, unsigned int key_bias, ProjCam c,
                 uint32_t *__restrict__ copy_s, float4 *__restrict__ copy_b, uint32_t *mark = nullptr,
                 const uint8_t *__restrict__ skip_cells = nullptr, int cells_w = 0)
 {
+    // MASKED (early pass, one pixel per thread): grid.y = pixel row, so the cell mask is indexed without a division
     const unsigned int stride = gridDim.x * blockDim.x;
-    const unsigned int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int xm = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int q0 = MASKED ? blockIdx.y * (unsigned int)res_x + xm : xm;
     uint32_t word[kScatterPix]; float4 pc[kScatterPix]; bool live[kScatterPix];
 #pragma unroll
     for (int i = 0; i < kScatterPix; ++i) {
         const unsigned int q = q0 + i * stride;
         live[i] = q < nsrc;
-        if (skip_cells && live[i]) {                     // early pass: the hole rays still own these 2x2 cells (k_list_scatter follows)
-            const unsigned int y = q / (unsigned int)res_x, x = q - y * (unsigned int)res_x;
-            live[i] = skip_cells[(size_t)(y >> 1) * cells_w + (x >> 1)] == 0;
-        }
+        if (MASKED)                                       // early pass: the hole rays still own these 2x2 cells (k_list_scatter follows)
+            live[i] = i == 0 && xm < (unsigned int)res_x && q < nsrc &&
+                      skip_cells[(blockIdx.y >> 1) * (unsigned int)cells_w + (xm >> 1)] == 0;
         word[i] = kHole; pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live[i]) {
             word[i] = ld_stream(screen + q + src0);

@@ -1040,7 +1040,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         CU_CHECK(cudaStreamWaitEvent(c->stream5, c->ev_gather_done, 0));
         {
             LAUNCH_ON(c, "k_proj_scatter2", c->stream5);
-            k_proj_scatter2<<<(n + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream5>>>(screen, back, c->key, res_x, res_y, 0u, n, 2u * n, pc,
+            k_proj_scatter2<true><<<dim3((unsigned)(res_x + 255) / 256, (unsigned)res_y), 256, 0, c->stream5>>>(screen, back, c->key, res_x, res_y, 0u, n, 2u * n, pc,
                 screen + 2 * (size_t)n, reinterpret_cast<float4 *>(back) + 2 * (size_t)n, nullptr, c->cell_mask, cells_w);
         }
         CU_CHECK(cudaEventRecord(c->ev_early_done, c->stream5));
@@ -1054,7 +1054,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     } else if (!rotate) {   // :177-198 source buffers in ascending offset = the reference's launch order (+ :394-405 of the previous frame)
         LAUNCH(c, "k_proj_scatter2");
         const unsigned int nsrc = from0 ? n : (unsigned int)src_count * n;
-        k_proj_scatter2<<<(nsrc + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
+        k_proj_scatter2<false><<<(nsrc + 256 * svo::kScatterPix - 1) / (256 * svo::kScatterPix), 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, from0 ? 0u : (unsigned int)src_first * n,
                                                                   nsrc, from0 ? 2u * n : 0u, pc, from0 ? screen + 2 * (size_t)n : nullptr,
                                                                   from0 ? reinterpret_cast<float4 *>(back) + 2 * (size_t)n : nullptr);
     } else {
@@ -1067,9 +1067,9 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
             LAUNCH(c, "k_proj_scatter2");
             const bool carried = from0 && slot == lazy_slot;
             uint32_t *mark = (int)slot != target ? screen : nullptr;
-            if (carried) k_proj_scatter2<<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, 0u, n, slot * n, pc, screen + (size_t)slot * n,
+            if (carried) k_proj_scatter2<false><<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, 0u, n, slot * n, pc, screen + (size_t)slot * n,
                                                                      reinterpret_cast<float4 *>(back) + (size_t)slot * n, mark);
-            else         k_proj_scatter2<<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, slot * n, n, 0u, pc, nullptr, nullptr, mark);
+            else         k_proj_scatter2<false><<<grid, 256, 0, c->stream>>>(screen, back, c->key, res_x, res_y, slot * n, n, 0u, pc, nullptr, nullptr, mark);
         }
     }
     if (!split) join_fill();

@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 1
 # DRAM bytes per launch with the caches left as the pipeline leaves them (one pass per kernel, no flush)
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum --cache-control none --clock-control none -s 40 -c 160 --csv \
     --log-file gpurun_out/${TAG}_dram_inpipeline.csv $B > gpurun_out/ncu_dram.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_rays|k_proj_scatter2|k_resolve_gather|k_copy_colorize|k_fill_list|k_hole_ids' -s 30 -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_rays|k_proj_scatter2|k_resolve_gather|k_copy_colorize|k_fill_list|k_hole_ids|k_list_scatter' -s 30 -c 14 \
     -o gpurun_out/${TAG}_prof_frame -f $B > gpurun_out/ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_raycast_fine_2' -c 2 \
     -o gpurun_out/${TAG}_prof_fullray -f python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras --profile-frames 1 > gpurun_out/ncu_fullray.log 2>&1
