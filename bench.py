@@ -600,6 +600,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the GPU output with the CPU reference (development aid)")
     ap.add_argument("--parity-frames", type=int, default=12, help="frames 0.. of the flythrough compared with the serial reference")
+    ap.add_argument("--e2e-pack", action="store_true", help="development aid: e2e frames packed to RGB24 by a pass on the copy stream "
+                    "(svo_present_rgb24_async) instead of by the producing kernels (SVO_FRAME_TEX_RGB24)")
     ap.add_argument("--debug-switches", default="", help="development aid: schedule A/B switches for svo_debug_set, e.g. no_split_resolve=1,holes_smax=32")
     ap.add_argument("--profile-frames", type=int, default=32)
     ap.add_argument("--stripe-rows", type=int, default=64, help="screen-band stripe height of the 3840x2160 band measurements (0 = contiguous bands)")
@@ -745,7 +747,7 @@ def main():
             # host -> device: the frame's camera block (kernel arguments); device -> host: the finished colorized frame as R,G,B
             # bytes (what the headless writer puts into a PPM), read back on the copy stream while the next frames render.  The
             # caller owns frame f-2 after its present_wait.
-            k = rc.draw_present(P[f], host_frames, rgb24=True)
+            k = rc.draw_present(P[f], host_frames, rgb24="pack" if args.e2e_pack else True)
             if f - (DEPTH - 1) >= args.warmup:
                 ocl.present_wait((f - (DEPTH - 1)) % DEPTH)
         for f in range(max(args.warmup, total - (DEPTH - 1)), total):

@@ -115,7 +115,7 @@ typedef struct svo_frame_params {
     float rows[3][4];            /* vx,vy,vz = rows of m    (raycast_proj)            src/raycast.h:160-162 */
     float cols[3][4];            /* vx,vy,vz = columns of m (ray kernels)             src/raycast.h:322-325 */
     float fovx, fovy;            /*                                                   src/raycast.h:109-110 */
-    int   flags;                 /* 0, SVO_FRAME_PINGPONG or SVO_FRAME_CACHE_ROTATION */
+    int   flags;                 /* 0 or SVO_FRAME_* flags below */
 } svo_frame_params;
 
 /* SVO_FRAME_PINGPONG: do not copy the frame into cache buffer 2 (src/raycast.h:394-405); instead render alternately into
@@ -127,7 +127,13 @@ enum { SVO_FRAME_PINGPONG = 1,
         * instead of the hard-wired 2: cache buffers 1 and 2 alternate every 16 frames, so both reprojection launches see real
         * frames (the triple buffer of SURVEY.md 8(f) rank 4).  Every buffer ends the frame as that variant of the reference
         * leaves it.  Not combinable with SVO_FRAME_PINGPONG. */
-       SVO_FRAME_CACHE_ROTATION = 2 };
+       SVO_FRAME_CACHE_ROTATION = 2,
+       /* SVO_FRAME_TEX_RGB24: `screenbuffer_tex` receives the colorized frame (raycast_colorize, kernel/kernel.cl:944-974) as
+        * packed R,G,B bytes, 3 per pixel, row-major -- the payload of a binary PPM / raw video frame -- stored by the
+        * kernels that produce the pixels, instead of the PBO's 0x00RRGGBB words (src/raycast.h:449-472).  The headless writer
+        * then reads the frame back with svo_present_async(host, tex, 3 * pixels, slot): no pack pass, 25 % less PCIe
+        * traffic.  The buffer needs 3 * res_x * res_y bytes.  Combinable with the other flags. */
+       SVO_FRAME_TEX_RGB24 = 4 };
 
 /* One whole frame on buffers laid out as the reference's (4 colour + 4 coordinate buffers at stride
  * res_x*res_y, id buffer, octree, colorize target).  Asynchronous; svo_end_all_kernels() waits.

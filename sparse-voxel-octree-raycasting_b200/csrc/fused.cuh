@@ -50,6 +50,7 @@ struct FusedScratch {
     uint32_t *resid;                  // pixel offsets of the hole pixels left for the gap filter
     unsigned int *resid_count;        // this frame's counter
     uint32_t *tex;                    // != nullptr: every kernel that writes a colour word also writes its colorized form here
+    uint32_t tex_rgb24;               // != 0: ... as packed R,G,B bytes (store_colorized)
 };
 
 struct PatchList {                    // gap-filter results, one word per pixel, defined for the in-bounds hole pixels
@@ -270,7 +271,7 @@ k_resolve_gather(const GatherArgs a)
             if (inr && a.stage_s) {                              // the tile ray's result, staged
                 const uint32_t w = a.stage_s[p];
                 dscreen[p] = w;
-                if (a.s.tex) a.s.tex[p] = colorize_word(w);
+                if (a.s.tex) store_colorized(a.s.tex, p, w, a.s.tex_rgb24 != 0);
                 dback[p * 4] = a.stage_b[p * 4]; dback[p * 4 + 1] = a.stage_b[p * 4 + 1]; dback[p * 4 + 2] = a.stage_b[p * 4 + 2];
             }
             if (v) {
@@ -282,12 +283,12 @@ k_resolve_gather(const GatherArgs a)
                 else {
                     const uint32_t w = (uint32_t)(k >> 32) + (col & 255u);
                     dscreen[p] = w;
-                    if (a.s.tex) a.s.tex[p] = colorize_word(w);
+                    if (a.s.tex) store_colorized(a.s.tex, p, w, a.s.tex_rgb24 != 0);
                     *reinterpret_cast<float4 *>(dback + p * 4) = make_float4(pc.x, pc.y, pc.z, phz);
                 }
             } else if (!inr) {
                 dscreen[p] = kHole;
-                if (a.s.tex) a.s.tex[p] = colorize_word(kHole);
+                if (a.s.tex) store_colorized(a.s.tex, p, kHole, a.s.tex_rgb24 != 0);
                 if (x > 1 && y > 1 && x < res_x - 1 && y < res_y - 1) a.s.resid[atomicAdd(a.s.resid_count, 1u)] = (uint32_t)p;
             }
         }
@@ -379,10 +380,10 @@ k_resolve_gather(const GatherArgs a)
                 const bool w0 = !inr[2 * r] || staged, w1 = !inr[2 * r + 1] || staged;
                 if (even && w0 && w1) {
                     *reinterpret_cast<uint2 *>(dscreen + p) = make_uint2(out[0], out[1]);
-                    if (a.s.tex) *reinterpret_cast<uint2 *>(a.s.tex + p) = make_uint2(colorize_word(out[0]), colorize_word(out[1]));
+                    if (a.s.tex) store_colorized2(a.s.tex, p, out[0], out[1], a.s.tex_rgb24 != 0);
                 } else {
-                    if (w0) { dscreen[p] = out[0]; if (a.s.tex) a.s.tex[p] = colorize_word(out[0]); }
-                    if (w1) { dscreen[p + 1] = out[1]; if (a.s.tex) a.s.tex[p + 1] = colorize_word(out[1]); }
+                    if (w0) { dscreen[p] = out[0]; if (a.s.tex) store_colorized(a.s.tex, p, out[0], a.s.tex_rgb24 != 0); }
+                    if (w1) { dscreen[p + 1] = out[1]; if (a.s.tex) store_colorized(a.s.tex, p + 1, out[1], a.s.tex_rgb24 != 0); }
                 }
             }
         }
@@ -602,7 +603,7 @@ k_rays_holes(uint32_t *__restrict__ screen, float *__restrict__ back, const uint
         const uint32_t idxy = idb[w + idsize * 2];
         const int idx = (int)(idxy & 0xffffu), idy = (int)(idxy >> 16);
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex, fs.tex_rgb24 != 0);
     }
 }
 
@@ -621,7 +622,7 @@ k_rays_tile(uint32_t *__restrict__ screen, float *__restrict__ back, const uint3
         if (lx >= gx || ly >= gy) continue;
         const int idx = lx + add_x, idy = ly + add_y;
         if (idx >= res_x || idy >= res_y) continue;
-        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex);
+        trace_pixel<D, kRaysBlock, true>(screen, back, oct, root, res_x, res_y, idx, idy, cam, stack + threadIdx.x, fs.resid_count, fs.resid, fs.tex, fs.tex_rgb24 != 0);
     }
 }
 
@@ -657,14 +658,14 @@ k_copy_colorize(const uint32_t *__restrict__ src_s, const float4 *__restrict__ s
 // The gap filter on the listed hole pixels only (~1-3 % of the frame); third stream, beside the next frame's reprojection.
 __global__ void __launch_bounds__(256)
 k_fill_list(SnapView view, uint32_t *__restrict__ tex, const uint32_t *__restrict__ resid, const unsigned int *__restrict__ resid_count,
-            PatchList patch, int res_x)
+            PatchList patch, int res_x, bool tex24 = false)
 {
     const unsigned int cnt = resid_count[0];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const int p = (int)resid[i];
         if (view[p] == kHole) {                          // else: listed before a ray filled it
             const uint32_t f = fillhole2_view(view, p, res_x);
-            if (f != kHole && tex) tex[p] = colorize_word(f);
+            if (f != kHole && tex) store_colorized(tex, (size_t)p, f, tex24);
             patch.value[p] = f;
         }
     }

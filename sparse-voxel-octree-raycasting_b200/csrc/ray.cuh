@@ -145,6 +145,29 @@ __device__ __forceinline__ uint32_t colorize_word(uint32_t word)
     return (uint32_t)(b + g * 256 + r * 65536);
 }
 
+// The colorized image has two layouts: 0x00RRGGBB words (the reference's PBO payload) or, for the headless writer, packed
+// R,G,B bytes (the payload of a binary PPM / raw video frame) stored by the producers themselves -- no pack pass, no
+// word image (svo_frame_params.flags & SVO_FRAME_TEX_RGB24).
+__device__ __forceinline__ void store_colorized(uint32_t *__restrict__ tex, size_t p, uint32_t word, bool rgb24)
+{
+    const uint32_t c = colorize_word(word);
+    if (rgb24) {
+        uint8_t *o = reinterpret_cast<uint8_t *>(tex) + 3 * p;
+        o[0] = (uint8_t)(c >> 16); o[1] = (uint8_t)(c >> 8); o[2] = (uint8_t)c;
+    } else tex[p] = c;
+}
+// pixels p and p + 1, p even: one 8-byte store, or three 2-byte stores (3p is even)
+__device__ __forceinline__ void store_colorized2(uint32_t *__restrict__ tex, size_t p, uint32_t word0, uint32_t word1, bool rgb24)
+{
+    const uint32_t c0 = colorize_word(word0), c1 = colorize_word(word1);
+    if (rgb24) {
+        uint16_t *o = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(tex) + 3 * p);
+        o[0] = (uint16_t)(((c0 >> 16) & 255u) | (c0 & 0xff00u));
+        o[1] = (uint16_t)((c0 & 255u) | ((c1 >> 8) & 0xff00u));
+        o[2] = (uint16_t)(((c1 >> 8) & 255u) | ((c1 & 255u) << 8));
+    } else *reinterpret_cast<uint2 *>(tex + p) = make_uint2(c0, c1);
+}
+
 // One primary ray for pixel (idx, idy): ray set-up of raycast_holes :639-663 / raycast_fine_2 :883-908,
 // CAST_RAY :114-214, fetchColor, and the stores :686-693 / :932-939 (w of the coordinate buffer is not written).
 // `stack` points at this thread's column of the shared [D+2][STRIDE] array (STRIDE = threads per CTA).
@@ -157,7 +180,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
                                             const uint32_t *__restrict__ oct, uint32_t root, int res_x, int res_y,
                                             int idx, int idy, const RayCam &c, uint32_t *stack,
                                             unsigned int *resid_count = nullptr, uint32_t *resid = nullptr,
-                                            uint32_t *__restrict__ tex = nullptr)
+                                            uint32_t *__restrict__ tex = nullptr, bool tex24 = false)
 {
     constexpr int kScaleMax = 1 << (D + 1);            // SCALE_MAX :19
     constexpr int kDepthAnd = (1 << D) - 1;            // OCTREE_DEPTH_AND :13
@@ -254,7 +277,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;
-    if (tex) tex[ofs] = colorize_word(0xff000000u + col);              // fused frame: no separate colorize pass
+    if (tex) store_colorized(tex, ofs, 0xff000000u + col, tex24);      // fused frame: no separate colorize pass
     // a traced word can coincide with the hole marker (unmasked colour 0x00ffff00): the gap filter must see it
     if (resid && 0xff000000u + col == kHole && idx > 1 && idy > 1 && idx < res_x - 1 && idy < res_y - 1)
         resid[atomicAdd(resid_count, 1u)] = (uint32_t)ofs;

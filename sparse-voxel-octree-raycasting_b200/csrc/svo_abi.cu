@@ -956,6 +956,11 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     uint32_t *tex = screenbuffer_tex ? (uint32_t *)screenbuffer_tex->dptr : nullptr;
     const bool lazy = lazy_copy && !pingpong;
     fs.tex = (lazy || pingpong) ? tex : nullptr;
+    // SVO_FRAME_TEX_RGB24: the producers store packed R,G,B bytes (3 per pixel) instead of 0x00RRGGBB words
+    const bool tex24 = (p->flags & SVO_FRAME_TEX_RGB24) != 0;
+    if (tex24 && (!tex || !fs.tex)) { svo_fail(-63, "svo_frame_fused: SVO_FRAME_TEX_RGB24 needs an image buffer and the default (lazy-copy or ping-pong) schedule"); return; }
+    if (tex && screenbuffer_tex->bytes < (size_t)n * (tex24 ? 3 : 4)) { svo_fail(-61, "svo_frame_fused: image buffer too small for %dx%d", res_x, res_y); return; }
+    fs.tex_rgb24 = tex24 ? 1u : 0u;
 
     // Lazy cache copy (exact mode).  The previous fused frame left buffer 0 -> 2 pending (materialize_copy).  If nothing
     // has observed the buffers since, buffer 0 still holds that frame, and this frame's reprojection pass reads it there
@@ -1137,7 +1142,7 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
         {
             LAUNCH_ON(c, "k_fill_list", sf);
             const SnapView view = {dscreen, dscreen, (int)n};
-            k_fill_list<<<c->num_sms * 2, 256, 0, sf>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x);
+            k_fill_list<<<c->num_sms * 2, 256, 0, sf>>>(view, tex, fs.resid, fs.resid_count, c->patch, res_x, tex24);
         }
         CU_CHECK(cudaEventRecord(c->ev_fill_done, sf));
         c->fill_event_valid = true;

@@ -29,6 +29,7 @@ class FrameParams(C.Structure):
 
 FRAME_PINGPONG = 1
 FRAME_CACHE_ROTATION = 2
+FRAME_TEX_RGB24 = 4      # colorized frame as packed R,G,B bytes, stored by the producers (svo_b200.h)
 
 
 def _sig(name, res, *args):

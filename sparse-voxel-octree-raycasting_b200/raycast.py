@@ -218,11 +218,19 @@ def draw_present(p, host_frames, rgb24=False):
     k = p.frame % depth
     tex = S.present_tex[k]
     S.frame = p.frame
-    ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
-    if rgb24:
+    if rgb24 == "pack":                                  # word image + k_pack_rgb24 on the copy stream (A/B of the path below)
+        ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
         ocl.present_rgb24_async(host_frames[k], tex, p.res_x * p.res_y, k)
-    else:
-        ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 4, k)
+        return k
+    if rgb24:
+        # the kernels that produce the pixels store R,G,B bytes themselves (SVO_FRAME_TEX_RGB24): the read-back is a plain copy
+        q = type(p).from_buffer_copy(p)
+        q.flags |= ocl.FRAME_TEX_RGB24
+        ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, q)
+        ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 3, k)
+        return k
+    ocl.frame_fused(S.mem_screenbuffer, S.mem_backbuffer, S.mem_idbuffer, S.mem_octree, S.octree_root_normal, tex, p)
+    ocl.present_async(host_frames[k], tex, p.res_x * p.res_y * 4, k)
     return k
 
 

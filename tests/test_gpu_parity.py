@@ -322,25 +322,52 @@ def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
 
 @pytest.mark.parametrize("res", [(320, 192), (201, 121)])
 def test_present_rgb24(svo, orc, world, res):
-    """Headless present as R,G,B bytes (svo_present_rgb24_async): the packed frame equals the 0x00RRGGBB image byte for
-    byte; 201x121 has a pixel count that is not a multiple of four (tail path of the pack kernel)."""
+    """Headless present as R,G,B bytes, both ways: (a) SVO_FRAME_TEX_RGB24 -- the kernels that produce the pixels store the
+    packed bytes themselves and the read-back is a plain copy (draw_present(rgb24=True), what bench.py's e2e leg runs);
+    (b) svo_present_rgb24_async -- a 0x00RRGGBB word image packed by k_pack_rgb24 on the copy stream.  Both must equal the
+    word image of the same frame byte for byte, for observed and for back-to-back frames; 201x121 has an odd row length
+    (scalar store paths) and a pixel count that is not a multiple of four (tail path of the pack kernel)."""
     octree, root = world
     rx, ry = res
     n = rx * ry
     rc, ocl = svo.raycast, svo.ocl
+    nframes = 7
+    cams = [((10 + 0.25 * f, 22, 9 + 0.2 * f), (0.4, 0.7 + 0.01 * f, 0.0)) for f in range(nframes)]
+
+    def to_rgb(tex):
+        return np.stack([(tex >> 16) & 255, (tex >> 8) & 255, tex & 255], axis=1).astype(np.uint8)
+
     svo.ocl_exit()
     rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused")
-    host = [ocl.host_alloc(n * 3), ocl.host_alloc(n * 3)]
+    host = [ocl.host_alloc(n * 4), ocl.host_alloc(n * 4)]
     try:
-        for f in range(4):
-            rc.set_camera((10 + 0.25 * f, 22, 9 + 0.2 * f), (0.4, 0.7 + 0.01 * f, 0.0))
-            k = rc.draw_present(rc.prepare_params(rx, ry, f), host, rgb24=True)
+        words = []                                       # word images, frames observed one by one; (b) on each of them
+        for f, (pos, rot) in enumerate(cams):
+            rc.set_camera(pos, rot)
+            k = rc.draw_present(rc.prepare_params(rx, ry, f), host)
             ocl.present_wait(k)
-            got = np.frombuffer(host[k], dtype=np.uint8).reshape(n, 3).copy()
-            tex = (svo.raycast.S.mem_screenbuffer_tex2 if k else svo.raycast.S.mem_screenbuffer_tex).to_numpy(np.uint32, n)
-            exp = np.stack([(tex >> 16) & 255, (tex >> 8) & 255, tex & 255], axis=1).astype(np.uint8)
-            assert np.array_equal(got, exp), f"frame {f}"
+            tex = np.frombuffer(host[k], dtype=np.uint32)[:n].copy()
             assert tex.max() < (1 << 24)
+            words.append(tex)
+            src = svo.raycast.S.mem_screenbuffer_tex2 if k else svo.raycast.S.mem_screenbuffer_tex
+            ocl.present_rgb24_async(host[k], src, n, k)
+            ocl.present_wait(k)
+            assert np.array_equal(np.frombuffer(host[k], dtype=np.uint8)[:3 * n].reshape(n, 3), to_rgb(tex)), f"pack, frame {f}"
+    finally:
+        rc.raycast_exit()
+    rc.raycast_init(octree, root, max_w=rx, max_h=ry, mode="fused")
+    try:
+        for f, (pos, rot) in enumerate(cams):            # (a), back to back: frames 2.. run the early / lazy schedule
+            rc.set_camera(pos, rot)
+            if f >= 2:
+                ocl.present_wait(f & 1)
+                got = np.frombuffer(host[f & 1], dtype=np.uint8)[:3 * n].reshape(n, 3).copy()
+                assert np.array_equal(got, to_rgb(words[f - 2])), f"rgb24 producers, frame {f - 2}"
+            assert rc.draw_present(rc.prepare_params(rx, ry, f), host, rgb24=True) == (f & 1)
+        for f in range(nframes - 2, nframes):
+            ocl.present_wait(f & 1)
+            got = np.frombuffer(host[f & 1], dtype=np.uint8)[:3 * n].reshape(n, 3).copy()
+            assert np.array_equal(got, to_rgb(words[f])), f"rgb24 producers, frame {f}"
     finally:
         for h in host:
             ocl.host_free(h)
