@@ -600,6 +600,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the GPU output with the CPU reference (development aid)")
     ap.add_argument("--parity-frames", type=int, default=12, help="frames 0.. of the flythrough compared with the serial reference")
+    ap.add_argument("--e2e-depth", type=int, default=3, choices=(2, 3, 4), help="frames in flight of the e2e leg (host buffers / colorize targets)")
     ap.add_argument("--e2e-pack", action="store_true", help="development aid: e2e frames packed to RGB24 by a pass on the copy stream "
                     "(svo_present_rgb24_async) instead of by the producing kernels (SVO_FRAME_TEX_RGB24)")
     ap.add_argument("--debug-switches", default="", help="development aid: schedule A/B switches for svo_debug_set, e.g. no_split_resolve=1,holes_smax=32")
@@ -721,7 +722,7 @@ def main():
     del scr_all
 
     # ---- e2e: same frames again (fresh cache state), each finished frame read back into pinned host memory ----
-    DEPTH = 3                                                        # frames in flight: render f, pack f-1, copy f-2
+    DEPTH = args.e2e_depth                                           # frames in flight (default 3): render f, copy f-1, consume f-2
     host_frames = [ocl.host_alloc(n * 3) for _ in range(DEPTH)]
     rc.prepare_present(DEPTH)                                        # no allocation inside the timed loop
     E2E_PASSES = 3        # the loop waits on the host every frame and is sensitive to whatever else the box does: median of three passes
