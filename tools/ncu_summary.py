@@ -60,7 +60,8 @@ def main():
         out = json.load(open(sys.argv[2])) if os.path.exists(sys.argv[2]) else {}
         for k, v in acc.items():
             m = lambda j: sum(x[j] for x in v) / len(v)
-            out[k] = {"dram_bytes_per_launch": m(0), "launches_profiled": len(v),
+            keep = {f: out[k][f] for f in ("rays_per_launch", "rays_note") if k in out and f in out[k]}   # annotations survive a refresh
+            out[k] = {**keep, "dram_bytes_per_launch": m(0), "launches_profiled": len(v),
                       # issue roof of the traversal kernels (bench.py roofline): warp instructions issued, lanes active per instruction, issue slots busy
                       "warp_inst_per_launch": m(2), "thr_per_inst": m(3), "issue_active_pct": m(4),
                       "source": os.path.basename(rep) + " (ncu --set full, caches flushed before each replay)"}
