@@ -40,6 +40,24 @@ struct RayCam {                               // arguments shared by raycast_hol
 };
 
 __device__ __forceinline__ uint32_t ldg(const uint32_t *p) { return __ldg(p); }
+// A/B variants north_star names (tools/variants.sh; results in DESIGN.md section 7): node words fetched as the aligned 16-byte
+// quad that contains them (SVO_NODE_LOAD16), ancestor stack in registers instead of shared memory (SVO_REG_STACK)
+#ifndef SVO_NODE_LOAD16
+#define SVO_NODE_LOAD16 0
+#endif
+#ifndef SVO_REG_STACK
+#define SVO_REG_STACK 0
+#endif
+__device__ __forceinline__ uint32_t ldg_node(const uint32_t *__restrict__ oct, uint32_t idx)
+{
+#if SVO_NODE_LOAD16
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(oct) + (idx >> 2));
+    const uint32_t sel = idx & 3u;
+    return sel == 0 ? q.x : sel == 1 ? q.y : sel == 2 ? q.z : q.w;
+#else
+    return __ldg(oct + idx);
+#endif
+}
 // ancestor stack: 32-bit shared-window addresses kept in a register (a generic pointer makes the compiler rebuild the
 // window base -- S2R tid, S2UR CgaCtaId, ULEA, LEA -- on every pop)
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -69,7 +87,7 @@ __device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct
         const bool packed = blk && rekursion <= 2;                        // the two byte-packed levels, once per ray
         const uint32_t idx = (blk ? n + local_root : n) + (packed ? nadd >> 2 : nadd);
         uint32_t w = 0u;
-        if (!(packed && rekursion == 1)) w = ldg(oct + idx);
+        if (!(packed && rekursion == 1)) w = ldg_node(oct, idx);
         if (packed) w = ((w >> ((nadd & 3u) << 3)) & 255u) + 256u + (nadd << 9);
         return w;
     }
@@ -83,7 +101,7 @@ __device__ __forceinline__ uint32_t fetch_child(const uint32_t *__restrict__ oct
             return ((ldg(oct + (n + (nadd >> 2))) >> ((nadd & 3u) << 3)) & 255u) + 256u + (nadd << 9);
         }
     }
-    return ldg(oct + (n + nadd));
+    return ldg_node(oct, n + nadd);
 }
 
 // sum of popcounts of bytes 1..n-1 of a byte-packed record (the loops at kernel/kernel.cl:82-85,104-107).
@@ -214,11 +232,30 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     // Ancestors live in the shared stack: level r holds the node the ray is in at that level, levels D and D+1 the root
     // (the reference's `rekursion==11 -> both = root`, :208).  The reference's nodeid_before is therefore not carried
     // through the loop: outside a hit it is stack[rekursion+1], at a hit stack[rekursion].
+#if SVO_REG_STACK
+    uint32_t rstack[D + 2];                                           // fully unrolled selects keep it in registers
+    auto stack_put = [&](int level, uint32_t v) {
+#pragma unroll
+        for (int l = 0; l < D + 2; ++l) if (l == level) rstack[l] = v;
+    };
+    auto stack_get = [&](int level) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int l = 0; l < D + 2; ++l) if (l == level) v = rstack[l];
+        return v;
+    };
+#pragma unroll
+    for (int l = 0; l < D + 2; ++l) rstack[l] = root;
+    (void)stack;
+#else
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stack);
     asm volatile("" : "+r"(sbase));                                   // opaque: keep it in a register, do not rematerialise
     constexpr uint32_t kLevel = (uint32_t)STRIDE * 4u;                // bytes between two levels of one thread's column
-    sts_u32(sbase + D * kLevel, root);
-    sts_u32(sbase + (D + 1) * kLevel, root);
+    auto stack_put = [&](int level, uint32_t v) { sts_u32(sbase + (uint32_t)level * kLevel, v); };
+    auto stack_get = [&](int level) { return lds_u32(sbase + (uint32_t)level * kLevel); };
+    stack_put(D, root);
+    stack_put(D + 1, root);
+#endif
     SVO_TRIP_DECL
 
     // The reference's loop takes one of two branches per iteration (descend into an occupied child / step through an
@@ -238,7 +275,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
             if (rekursion <= lod) { hit = true; break; }               // :172
             SVO_TRIP_HOOK(1)
             --rekursion;
-            sts_u32(sbase + (uint32_t)rekursion * kLevel, nodeid);
+            stack_put(rekursion, nodeid);
         }
         if (hit) break;
         const float mx = (float)((cx + 1) << rekursion) - px;          // :181 step to the nearest face of the current cell
@@ -261,7 +298,7 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
             uint32_t top;                                              // index of the highest set bit (x0r != 0 here)
             asm("bfind.u32 %0, %1;" : "=r"(top) : "r"((uint32_t)x0r));
             rekursion = (int)top + 1;                                  // rekursion_new + 1  (<= D)
-            nodeid = lds_u32(sbase + (uint32_t)rekursion * kLevel);
+            nodeid = stack_get(rekursion);
             if (distance > lodswitch) { lodswitch *= 2.0f; ++lod; }    // :209
         }
         if ((x0ry & kScaleMax) != 0) break;                            // :211 the ray left the world through y
@@ -272,8 +309,8 @@ __device__ __forceinline__ void trace_pixel(uint32_t *__restrict__ screen, float
     if (sign_xyz & 2) py = (float)kScaleMax - py;
     if (sign_xyz & 4) pz = (float)kScaleMax - pz;
 
-    const uint32_t before2 = lds_u32(sbase + (uint32_t)(rekursion + 1) * kLevel);
-    const uint32_t before = hit ? lds_u32(sbase + (uint32_t)rekursion * kLevel) : before2;
+    const uint32_t before2 = stack_get(rekursion + 1);
+    const uint32_t before = hit ? stack_get(rekursion) : before2;
     const uint32_t col = fetch_color(oct, nodeid, before, before2, local_root, rekursion, node_test);
     const size_t ofs = (size_t)idy * res_x + idx;
     screen[ofs] = 0xff000000u + col;
