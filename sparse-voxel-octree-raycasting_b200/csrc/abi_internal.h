@@ -32,6 +32,7 @@ struct svo_ctx_s {
     cudaStream_t stream5 = nullptr;
     cudaEvent_t ev_early_done = nullptr;
     uint8_t *cell_mask = nullptr; size_t cell_mask_bytes = 0;
+    int mask_res_x = 0, mask_res_y = 0;     // resolution whose cell layout the mask currently has
     bool early_ready = false;               // the last fused frame left a mask + id list that describe its pending cells
     int early_res_x = 0, early_res_y = 0;
     const uint32_t *early_idb = nullptr;

@@ -999,11 +999,17 @@ extern "C" void svo_frame_fused(svo_mem_t screenbuffer, svo_mem_t backbuffer, sv
     const bool early_capable = split && staged && lazy && !rotate && nb > 0 && !g_dbg.no_early_scatter;
     const bool early = early_capable && from0 && c->early_ready && c->early_res_x == res_x && c->early_res_y == res_y &&
                        c->early_idb == idb;
-    if (early_capable && c->cell_mask_bytes < mask_bytes) {                // (never while an early pass could be reading it: !early here)
-        if (c->cell_mask) { for (cudaStream_t st : {c->stream, c->stream5}) CU_CHECK(cudaStreamSynchronize(st)); CU_CHECK(cudaFree(c->cell_mask)); }
-        CU_CHECK(cudaMalloc(&c->cell_mask, mask_bytes));
-        CU_CHECK(cudaMemsetAsync(c->cell_mask, 0, mask_bytes, c->stream));  // cells outside the whole 16x16 blocks stay 0
-        c->cell_mask_bytes = mask_bytes;
+    if (early_capable && (c->cell_mask_bytes < mask_bytes || c->mask_res_x != res_x || c->mask_res_y != res_y)) {
+        // new size or new layout (never while an early pass could be reading the mask: `early` is false here, and the main
+        // stream has joined every earlier early pass).  k_hole_ids writes the cells of the whole 16x16 blocks only: the
+        // cells of the right / bottom strips must be 0 and would otherwise keep bytes of another resolution's layout
+        if (c->cell_mask_bytes < mask_bytes) {
+            if (c->cell_mask) { for (cudaStream_t st : {c->stream, c->stream5}) CU_CHECK(cudaStreamSynchronize(st)); CU_CHECK(cudaFree(c->cell_mask)); }
+            CU_CHECK(cudaMalloc(&c->cell_mask, mask_bytes));
+            c->cell_mask_bytes = mask_bytes;
+        }
+        CU_CHECK(cudaMemsetAsync(c->cell_mask, 0, mask_bytes, c->stream));
+        c->mask_res_x = res_x; c->mask_res_y = res_y;
     }
     auto launch_tile = [&](cudaStream_t st) {                              // :361-387 tile refresh
         LAUNCH_ON(c, "k_rays_tile", st);

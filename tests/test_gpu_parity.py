@@ -320,6 +320,53 @@ def test_frame_sequence_back_to_back(svo, orc, world, res, nframes, observe):
         svo.ocl_init(0)
 
 
+def test_resolution_change_back_to_back(svo, orc, world):
+    """A host that changes the resolution inside one context (the reference's window resize): 5 frames at 320x192, then the
+    frame counter restarts and 7 frames at 200x120 follow, all back to back.  200x120 has right / bottom strips outside the
+    whole 16x16 blocks, which the early reprojection pass must not skip: its cell mask is laid out per resolution and the
+    strip cells are never written by the id pass, so bytes of the 320x192 layout must not survive the change."""
+    octree, root = world
+    rc, ocl = svo.raycast, svo.ocl
+    svo.ocl_exit()
+    rc.raycast_init(octree, root, max_w=320, max_h=192, mode="fused")
+    host = [ocl.host_alloc(320 * 192 * 4), ocl.host_alloc(320 * 192 * 4)]
+    try:
+        for (rx, ry), nframes in (((320, 192), 5), ((200, 120), 7)):
+            n = rx * ry
+            O = ofr.OracleFrame(orc, octree, root, rx, ry, threads=os.cpu_count() or 4)
+            params = []
+            for f in range(nframes):
+                pos, rot = (10 + 0.25 * f, 22 + 0.05 * f, 9 + 0.2 * f), (0.4 + 0.002 * f, 0.7 + 0.01 * f, 0.0)
+                O.draw(pos, rot)
+                rc.set_camera(pos, rot)
+                params.append(rc.prepare_params(rx, ry, f))
+            base = ocl.frame_early_count()
+            for f in range(nframes):
+                if f >= 2:
+                    ocl.present_wait(f & 1)
+                rc.draw_present(params[f], host)
+            for f in range(max(0, nframes - 2), nframes):
+                ocl.present_wait(f & 1)
+            assert ocl.frame_early_count() - base == nframes - 2
+            got = np.frombuffer(host[(nframes - 1) & 1], dtype=np.uint32)[:n].copy()
+            assert np.array_equal(got, O.tex), f"{rx}x{ry} tex"
+            screen, back, idb = rc.read_buffers(rx, ry)
+            assert rc.idbuf_size() == O.idbuf_size
+            assert np.array_equal(idb[:2 * O.nblocks + O.idbuf_size], O.idbuf[:2 * O.nblocks + O.idbuf_size]), f"{rx}x{ry} ids"
+            assert np.array_equal(screen, O.screen[:4 * n]), f"{rx}x{ry} colour"
+            # positions: the words a frame defines (xyz of the non-hole pixels of buffers 0 and 2); the rest of the coordinate
+            # buffers still holds the other resolution's data here and zeros in the freshly started oracle
+            got_b, exp_b = back.view(np.uint32).reshape(4, n, 4), O.back[:16 * n].view(np.uint32).reshape(4, n, 4)
+            for slot in (0, 2):
+                live = screen[slot * n:(slot + 1) * n] != 0xffffff00
+                assert np.array_equal(got_b[slot][live][:, :3], exp_b[slot][live][:, :3]), f"{rx}x{ry} xyz of buffer {slot}"
+    finally:
+        for h in host:
+            ocl.host_free(h)
+        rc.raycast_exit()
+        svo.ocl_init(0)
+
+
 @pytest.mark.parametrize("res", [(320, 192), (201, 121)])
 def test_present_rgb24(svo, orc, world, res):
     """Headless present as R,G,B bytes, both ways: (a) SVO_FRAME_TEX_RGB24 -- the kernels that produce the pixels store the
