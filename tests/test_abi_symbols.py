@@ -41,6 +41,19 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, missing
 
 
+def test_python_mirror_matches_the_header():
+    """The ctypes mirror binds every frame-level entry point the header declares and uses the header's flag values."""
+    text = open(os.path.join(ROOT, "include", "svo_b200.h")).read()
+    flags = {k: int(v) for k, v in re.findall(r"\b(SVO_FRAME_[A-Z0-9_]+)\s*=\s*(\d+)", re.sub(r"/\*.*?\*/", "", text, flags=re.S))}
+    assert flags == {"SVO_FRAME_PINGPONG": 1, "SVO_FRAME_CACHE_ROTATION": 2, "SVO_FRAME_TEX_RGB24": 4}
+    mirror = open(os.path.join(ROOT, "sparse-voxel-octree-raycasting_b200", "ocl.py")).read()
+    for name, value in flags.items():
+        assert re.search(rf"^{name[4:]}\s*=\s*{value}\b", mirror, flags=re.M), name
+    for sym in ("svo_frame_fused", "svo_frame_deferred_count", "svo_frame_early_count", "svo_present_async", "svo_present_rgb24_async",
+                "svo_present_wait", "svo_raycast_batch", "svo_debug_set"):
+        assert f'"{sym}"' in mirror, sym
+
+
 def test_round_up(lib):
     lib.svo_round_up.restype = ctypes.c_size_t
     assert lib.svo_round_up(16, 240) == 240 and lib.svo_round_up(16, 540) == 544 and lib.svo_round_up(256, 1) == 256
