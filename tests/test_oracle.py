@@ -203,3 +203,46 @@ def test_threaded_baseline_kernels_match_serial(which, orc, ref):
     # racy projection: same id counts within a small margin, and the images agree on almost every pixel
     same = np.count_nonzero(A.tex == B.tex) / n
     assert same > 0.99, same
+
+
+def test_trip_log_is_consistent_and_side_effect_free(orc):
+    """The analysis hooks of the oracle (tools/warp_sim.py reads them): with the per-pixel trip log and iteration buffer
+    switched on a full-screen raycast produces the same words, and every ray's log adds up to its iteration count
+    (descents + steps; the last entry of a ray that ends by a hit has no step)."""
+    import ctypes as C
+    octree, root = orc.build_octree(*scenes.small_world())
+    rx, ry, stride = 160, 96, 200
+    n = rx * ry
+    cam = fr.camera_args((10.0, 22.0, 9.0), (0.4, 0.7, 0.0))
+
+    def shoot():
+        screen = np.zeros(4 * n + 64, dtype=np.uint32)
+        back = np.zeros(16 * n + 64, dtype=np.float32)
+        orc.raycast_fine_2(screen, back, octree, root, rx, ry, 0, 0, 0, cam["v0"], *cam["cols"], threads=2, gx=rx, gy=ry)
+        return screen[:n].copy(), back[:4 * n].copy()
+
+    plain_s, plain_b = shoot()
+    log = np.zeros((n, stride), dtype=np.uint8)
+    iters = np.zeros(n, dtype=np.uint32)
+    orc.lib.orc_set_trip_log.argtypes = [C.c_void_p, C.c_int]
+    orc.lib.orc_set_iter_buffer.argtypes = [C.c_void_p]
+    orc.lib.orc_set_trip_log(log.ctypes.data, stride)
+    orc.lib.orc_set_iter_buffer(iters.ctypes.data)
+    try:
+        got_s, got_b = shoot()
+    finally:
+        orc.lib.orc_set_trip_log(None, 0)
+        orc.lib.orc_set_iter_buffer(None)
+    assert np.array_equal(got_s, plain_s) and np.array_equal(got_b.view(np.uint32), plain_b.view(np.uint32))
+    last = (log & 0x80) != 0
+    assert (last.sum(axis=1) == 1).all()                                 # exactly one end marker per ray
+    ntrips = last.argmax(axis=1) + 1
+    assert ntrips.max() < stride - 1                                     # no ray was truncated at this size
+    desc = np.where(np.arange(stride)[None, :] < ntrips[:, None], log & 0x7f, 0).astype(np.int64)
+    total_desc = desc.sum(axis=1)
+    last_desc = desc[np.arange(n), ntrips - 1]
+    # steps: one per entry, except a final entry that holds descents (the ray ended inside the descent loop or right after
+    # its last step's break) -- the iteration count lies between the two readings
+    lo, hi = total_desc + ntrips - (last_desc > 0), total_desc + ntrips
+    assert ((iters >= lo) & (iters <= hi)).all()
+    assert total_desc.sum() > 10 * n                                     # the scene is not empty
